@@ -1,0 +1,181 @@
+/*
+ * moip_b200.h -- C ABI of the B200-native solver core behind moip_aira's hot path.
+ *
+ * Drop-in boundary ("Seam 2"): every entry point below replaces one
+ * reference interface, cited as file:line relative to the reference tree.  Conventions follow
+ * the CPLEX callable library the reference binds today: plain pointers and sizes, caller-owned
+ * buffers (the library copies), `int` return 0 = OK (nonzero = error, diagnostic on stderr),
+ * no exceptions across the boundary, one context per worker thread (a context is used by its
+ * owner only; several contexts may share one GPU).
+ *
+ * There is no CPU fallback behind any compute entry point: they return MOIP_ERR_CUDA when no
+ * sm_100 device / kernel image is usable.
+ */
+#ifndef MOIP_B200_H
+#define MOIP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status / error codes -------------------------------------------------------------- */
+#define MOIP_OK 0
+#define MOIP_ERR_ARG 1
+#define MOIP_ERR_PARSE 2
+#define MOIP_ERR_CUDA 3
+#define MOIP_ERR_UNSUPPORTED 4
+#define MOIP_ERR_LIMIT 5
+/* MIP statuses: the values the reference compares against after CPXgetstat
+ * (src/aira.cpp:489-492, :644, :840).  Kept numerically equal to CPLEX's so that
+ * `solnstat == CPXMIP_INFEASIBLE` keeps working when solve() forwards our status. */
+#define MOIP_MIP_OPTIMAL 101
+#define MOIP_MIP_INFEASIBLE 103
+#define MOIP_MIP_INFORUNBD 119
+/* node-LP statuses (no reference counterpart: node LPs live inside CPXmipopt, src/aira.cpp:480) */
+#define MOIP_LP_CONVERGED 0   /* relative KKT error <= eps                              */
+#define MOIP_LP_CUTOFF 1      /* valid dual bound reached the cutoff (node can be pruned) */
+#define MOIP_LP_ITERLIMIT 2   /* iteration cap; dual bound is still valid                */
+#define MOIP_LP_INFEASIBLE 3  /* dual bound exceeded the objective's upper bound on the box */
+
+#define MOIP_SENSE_MIN 0 /* reference src/sense.h:4 */
+#define MOIP_SENSE_MAX 1
+#define MOIP_INFBOUND 1.0E+20 /* CPX_INFBOUND; "no bound" in rhs[] (src/problem.cpp:126) */
+#define MOIP_MAX_OBJ 4        /* reference supports objcnt < maxObjCount = 5 (src/aira.cpp:230) */
+
+typedef struct moip_model moip_model; /* replaces Problem + the CPXLPptr model (src/problem.h, src/env.h:6-10) */
+typedef struct moip_ctx moip_ctx;     /* replaces one worker's Env (CPXENVptr + CPXLPptr copy, src/aira.cpp:541-585) */
+typedef struct moip_cache moip_cache; /* replaces Solutions (src/solutions.h:10-36) */
+
+typedef struct {
+  int n;        /* columns                     (CPXgetnumcols, src/problem.cpp:47)            */
+  int ms;       /* structural rows (without the k objective-bound rows)                        */
+  int k;        /* objcnt                      (src/problem.cpp:61)                            */
+  int nnz;      /* structural nonzeros                                                         */
+  int sense;    /* MOIP_SENSE_*               (src/problem.cpp:119-120)                        */
+  int all_binary;
+  int m;        /* ms + k = rows of the LP the kernels see                                     */
+  int mask_words; /* uint32 words of one 2-bit/var fixing mask = ceil(n/16)                    */
+} moip_model_info;
+
+/* ---- model: replaces Problem::Problem + CPXreadcopyprob (src/problem.cpp:12-154, :157-340) - */
+int moip_model_load(const char* path, moip_model** out);
+void moip_model_free(moip_model* m);
+int moip_model_get_info(const moip_model* m, moip_model_info* info);
+/* Problem::objcoef[obj][0..n) (src/problem.cpp:73-107) */
+int moip_model_objcoef(const moip_model* m, int obj, double* out_n);
+/* structural part, dense row-major ms*n, row sense chars 'L','G','E', rhs, column bounds/integrality */
+int moip_model_dense(const moip_model* m, double* a_ms_n, char* row_sense_ms, double* rhs_ms,
+                     double* lb_n, double* ub_n, uint8_t* is_int_n);
+int moip_model_colname(const moip_model* m, int j, char* buf, int buflen); /* CPXgetcolname, src/problem.cpp:183 */
+
+/* ---- context: one per worker (src/aira.cpp:561-585). `stream` is a cudaStream_t (NULL = default). */
+int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx** out);
+void moip_ctx_destroy(moip_ctx* c);
+
+/* ---- K1: batched node-LP relaxations (inside CPXmipopt today, src/aira.cpp:480) ------------- */
+typedef struct {
+  double eps;        /* relative KKT tolerance for MOIP_LP_CONVERGED (default 1e-8)         */
+  int max_iter;      /* iteration cap per node (default 100000)                              */
+  int check_every;   /* KKT / dual-bound evaluation cadence in iterations (default 32)       */
+  int fixed_iters;   /* >0: run exactly this many iterations, no termination tests (roofline) */
+  double cutoff;     /* stop with MOIP_LP_CUTOFF once dual bound >= cutoff (internal min-form; use MOIP_INFBOUND to disable) */
+} moip_lp_params;
+void moip_lp_default_params(moip_lp_params* p);
+
+/* Host-buffer call (the e2e path): B node LPs  min/max objective[cost_idx[b]]
+ * s.t. structural rows, objective-bound rows with rhs[b][0..k) (+-1e20 = free),
+ * columns fixed by fix_masks[b] (2 bits per column: 0 free, 2 fixed to 0, 3 fixed to 1).
+ * Outputs (all optional except status): objective value of the primal iterate and the valid
+ * Lagrangian bound in the model's own sense/sign, status (MOIP_LP_*), iterations, x[b][0..n). */
+int moip_lp_batch_solve(moip_ctx* c, int B, const int* cost_idx, const double* rhs,
+                        const uint32_t* fix_masks, const moip_lp_params* params,
+                        double* primal_obj, double* dual_bound, int* status, int* iters,
+                        double* x_out);
+/* Resident variant: upload once, run many times (bench `value`), download. */
+int moip_lp_batch_upload(moip_ctx* c, int B, const int* cost_idx, const double* rhs,
+                         const uint32_t* fix_masks);
+int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params);         /* async on the ctx stream */
+int moip_lp_batch_download(moip_ctx* c, double* primal_obj, double* dual_bound, int* status,
+                           int* iters, double* x_out);                     /* syncs the stream */
+
+/* ---- K3: solution cache (src/solutions.cpp:11-101, src/solutions.h:41-57) ------------------- */
+int moip_cache_create(moip_ctx* c, moip_cache** out);
+void moip_cache_destroy(moip_cache* s);
+/* Solutions::insert (src/solutions.cpp:82-101); result may be NULL when infeasible */
+int moip_cache_insert(moip_cache* s, const double* ip, const int* result, int infeasible);
+int moip_cache_size(const moip_cache* s);
+/* Solutions::find for Q queries at once (src/solutions.cpp:11-81): first_match[q] = insertion
+ * index of the first record that is a still-valid relaxation of ip[q][0..k), or -1. */
+int moip_cache_find_batch(moip_cache* s, int Q, const double* ip, int sense, int* first_match);
+/* read record i back (what the caller does through the returned Result*, src/aira.cpp:826-827) */
+int moip_cache_get(const moip_cache* s, int i, double* ip, int* result, int* infeasible);
+/* Solutions::merge (src/solutions.h:41-44): splice `other` in front of `s`, leaving it empty */
+int moip_cache_merge(moip_cache* s, moip_cache* other);
+/* Solutions::sort_unique + the row dump of main (src/solutions.h:54-57, src/aira.cpp:336-346):
+ * returns the number of feasible rows, writes up to cap rows of k ints */
+int moip_cache_sort_unique(moip_cache* s, int* rows, int cap);
+
+/* ---- K4: exact int64 verification of integer points (round()/Sum c x of src/aira.cpp:517-530) */
+int moip_verify_int64(moip_ctx* c, int B, const int32_t* x, const double* rhs /* B*k or NULL */,
+                      int64_t* obj_out /* B*k */, uint8_t* feasible_out /* B */);
+
+/* ---- the solve: replaces the bodies of solve() and get_limit() ------------------------------ */
+/* int solve(Env&, Problem&, int* result, double* rhs, Thread* t)   (src/aira.cpp:452-536) */
+int moip_lex_solve(moip_ctx* c, const int* perm, int n_obj, const double* rhs, int* result,
+                   int* mip_status);
+/* void get_limit(Env&, Problem&, int obj, double* rhs, int* result, Sense) (src/aira.cpp:367-450);
+ * result is left untouched when infeasible, like the reference (:410-412). */
+int moip_get_limit(moip_ctx* c, int obj, int sense, const double* rhs, int* result, int* mip_status);
+
+/* counters (ipcount of src/aira.cpp:80 and the FINETIMING split of :554-560) */
+typedef struct {
+  int64_t ip_solved;      /* single-objective IPs solved (CPXmipopt calls in the reference) */
+  int64_t bb_nodes;       /* branch-and-bound nodes evaluated                               */
+  int64_t node_lps;       /* node LP relaxations solved on the GPU                          */
+  int64_t lp_iterations;  /* PDHG iterations summed over node LPs                           */
+  int64_t kernel_launches;/* kernels launched by this context                               */
+  int64_t cache_queries;  /* K3 queries                                                     */
+  double solver_seconds;  /* wall time inside lex_solve/get_limit                           */
+} moip_stats;
+int moip_ctx_stats(const moip_ctx* c, moip_stats* out);
+int moip_ctx_reset_stats(moip_ctx* c);
+
+/* ---- subproblem generator re-hosted on the boundary above (src/aira.cpp:538-1884 without the
+ * inter-thread bound cells, and the EPP driver src/aira.cpp:1886-1990) -------------------------- */
+typedef int (*moip_solve_fn)(void* user, const int* perm, int n_obj, const double* rhs, int* result,
+                             int* mip_status);
+/* cache callbacks for the host-logic test hook: find returns 1 (hit: fills infeasible/result), 0 (miss), <0 error */
+typedef int (*moip_find_cb)(void* user, const double* ip, int* infeasible, int* result);
+typedef int (*moip_insert_cb)(void* user, const double* ip, const int* result, int infeasible);
+typedef struct {
+  int id;
+  int n_obj;                 /* Thread::nObj()  (src/thread.h:41)  */
+  int perm[MOIP_MAX_OBJ];    /* Thread::perm(i) (src/thread.h:37)  */
+  int split;                 /* global `split`  (src/aira.cpp:38)  */
+  double split_start, split_stop; /* Thread::split_start/stop (src/thread.h:25-26) */
+} moip_worker;
+/* optimise<sense>() for one worker.  `all` / `infeasibles` are the two shared stores of
+ * src/aira.cpp:539; found points are merged into `all` (:1877-1879). */
+int moip_optimise(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles);
+/* same state machine with caller-supplied solve/find/insert (host-logic tests without a GPU; the
+ * product path is moip_optimise, which binds them to the GPU solve and the K3 scan) */
+int moip_optimise_with(int k, int sense, const moip_worker* w, moip_solve_fn solve, moip_find_cb find,
+                       moip_insert_cb insert, void* user, int64_t* n_iterations, int64_t* n_hits);
+/* strip edges of split_optimise (src/aira.cpp:1886-1917): writes num_threads (start,stop) pairs */
+int moip_split_strips(int sense, int biggest, int smallest, int num_threads, int split_normal,
+                      double* start_stop);
+/* whole program: what main() computes (src/aira.cpp:264-346).  split=0: one synergistic worker
+ * with the identity permutation (-t 1); split=1: EPP with num_threads strips solved one after
+ * another on this context (multi-GPU runs shard the strips across ranks).
+ * rows_out receives the sorted, de-duplicated front (k ints per row). */
+int moip_pareto_front(moip_ctx* c, int split, int num_threads, int split_normal, int* rows_out,
+                      int cap, int* n_rows);
+
+const char* moip_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOIP_B200_H */

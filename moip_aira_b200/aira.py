@@ -1,0 +1,192 @@
+"""`aira` command-line mirror (reference src/aira.cpp:140-364) on top of the C ABI.
+
+    python -m moip_aira_b200.aira -p Examples/3KP10.lp [-o out] [--split] [--split-normal] [-t N] [-c N] [-s]
+
+Options, defaults, output-file naming and the `.out` layout follow the reference (options :159-188,
+naming :213-221, writer :252, :336-358).  `-c` (CPLEX threads) is accepted and ignored: there is no
+CPLEX.  Without --split one worker with the identity permutation runs on this rank's GPU (the
+inter-worker bound protocol of -t N > 1 is not re-hosted yet: SURVEY.md section 8f-3; the front is the
+same).  With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded over the ranks
+of a torch.distributed job (one rank per GPU, `torchrun --nproc-per-node G`), with an all-gather of
+the points found between levels; a single process solves the strips one after another.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+INT_MAX, INT_MIN = 2147483647, -2147483648
+
+
+# ------------------------------------------------------------------------------------ distributed
+class Dist:
+    """Thin wrapper: rank/world from the environment, all-gather of variable-length int rows."""
+
+    def __init__(self, device=None):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.device = device
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                backend = "nccl" if device is not None else "gloo"
+                dist.init_process_group(backend=backend)
+            self.pg = dist
+
+    def allgather_rows(self, rows, k):
+        """rows: list of k-int tuples on this rank -> concatenation over ranks (rank order)."""
+        if self.world == 1:
+            return [tuple(r) for r in rows]
+        import torch
+        dev = self.device if self.device is not None else "cpu"
+        cnt = torch.tensor([len(rows)], dtype=torch.int64, device=dev)
+        cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        self.pg.all_gather(cnts, cnt)
+        mx = max(int(c.item()) for c in cnts)
+        buf = torch.zeros((max(mx, 1), k), dtype=torch.int32, device=dev)
+        if rows:
+            buf[:len(rows)] = torch.tensor(np.asarray(rows, dtype=np.int32).reshape(-1, k), device=dev)
+        bufs = [torch.zeros_like(buf) for _ in range(self.world)]
+        self.pg.all_gather(bufs, buf)
+        out = []
+        for c, b in zip(cnts, bufs):
+            out += [tuple(int(v) for v in r) for r in b[:int(c.item())].cpu().numpy()]
+        return out
+
+    def barrier(self):
+        if self.world > 1:
+            self.pg.barrier()
+
+
+# ------------------------------------------------------------------------------------ backends
+class GpuBackend:
+    """Product backend: one solver context on this rank's B200."""
+
+    def __init__(self, path, device=0, stream=None):
+        import moip_aira_b200 as mb
+        self.mb = mb
+        self.problem = mb.Problem(path)
+        self.ctx = mb.Context(self.problem, device=device, stream=stream)
+        self.k = self.problem.objcnt
+        self.sense = self.problem.objsen
+
+    def get_limit(self, obj, rhs):
+        st, res = self.ctx.get_limit(obj, rhs)
+        return res
+
+    def run_strips(self, n_obj, strips):
+        """The strips this rank owns at one EPP level, sharing `here`/`infeasibles` like the reference."""
+        mb = self.mb
+        here, inf = mb.Solutions(self.ctx), mb.Solutions(self.ctx)
+        for t, (a, b) in strips:
+            w = mb.make_worker(self.k, n_obj=n_obj, split=True, split_start=a, split_stop=b, wid=t)
+            self.ctx.optimise(w, here, inf)
+        rows = [here.get(i) for i in range(len(here))]
+        return [tuple(r[2]) for r in rows if not r[1]]
+
+    def sequential_front(self):
+        return self.ctx.pareto_front()
+
+    def split_strips(self, biggest, smallest, num_threads, split_normal):
+        return self.mb.split_strips(self.sense, biggest, smallest, num_threads, split_normal)
+
+    def ip_count(self):
+        return self.ctx.stats()["ip_solved"]
+
+
+def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):
+    """split_setup (src/aira.cpp:1945-1990) with each level's strips sharded over the ranks."""
+    k = be.k
+    is_min = be.sense == 0
+    free = [1e20 if is_min else -1e20] * k
+
+    def level(n_obj):
+        if n_obj == 1:
+            r = be.get_limit(0, free)
+            return [tuple(r)] if r is not None else []
+        lower = level(n_obj - 1)
+        if not lower:
+            return []
+        res = be.get_limit(n_obj - 1, free)
+        if res is None:
+            return []
+        if is_min:
+            smallest, biggest = res[n_obj - 1], max([INT_MIN] + [s[n_obj - 1] for s in lower])
+            if biggest == smallest:
+                biggest = INT_MAX
+        else:
+            biggest, smallest = res[n_obj - 1], min([INT_MAX] + [s[n_obj - 1] for s in lower])
+            if biggest == smallest:
+                smallest = INT_MIN
+        strips = be.split_strips(biggest, smallest, num_threads, split_normal)
+        mine = [(t, s) for t, s in enumerate(strips) if t % dist.world == dist.rank]
+        rows = be.run_strips(n_obj, mine) if mine else []
+        return dist.allgather_rows(rows, k)
+
+    rows = level(k)
+    return sorted(set(rows), key=lambda r: tuple(-v for v in r))     # sort_unique (src/aira.cpp:336)
+
+
+def format_out(front, cpu_s, wall_s, ips, tag):
+    lines = ["", f"Using improved algorithm at {tag}"]
+    lines += ["".join(f"{v}\t" for v in row) for row in front]
+    lines += ["", "---", f"{cpu_s:8.3f} CPU seconds", f"{wall_s:8.3f} elapsed seconds",
+              f"{ips:8d} IPs solved", f"{len(front):8d} Solutions found"]
+    return "\n".join(lines) + "\n"
+
+
+def main(argv=None, backend_factory=None):
+    ap = argparse.ArgumentParser(prog="aira", description="Options for aira")
+    ap.add_argument("-p", "--lp", dest="lp", help="The LP file to solve. Required.")
+    ap.add_argument("-o", "--output", dest="output", help="The output file. Optional.")
+    ap.add_argument("--split", action="store_true", help="Split the range of the last objective into one strip per thread")
+    ap.add_argument("--split-normal", action="store_true", dest="split_normal")
+    ap.add_argument("-s", "--spread", action="store_true", default=True)
+    ap.add_argument("-t", "--threads", type=int, default=1)
+    ap.add_argument("-c", "--cplex_threads", type=int, default=1)
+    args = ap.parse_args(argv)
+    if args.split_normal and args.threads > 12:
+        print("Error: split_normal can only handle at most 12 threads.", file=sys.stderr)
+        return 1
+    if not args.lp:
+        print("Error: You must pass in a problem file. All other parameters are optional.", file=sys.stderr)
+        ap.print_help()
+        return 1
+    out_path = args.output or (args.lp[:args.lp.rfind(".")] + ".out" if "." in args.lp else args.lp + ".out")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend_factory is None:
+        import torch
+        dev = None
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            torch.cuda.set_device(local_rank)
+            dev = torch.device("cuda", local_rank)
+        dist = Dist(dev)
+        be = GpuBackend(args.lp, device=local_rank)
+    else:
+        dist = Dist(None)
+        be = backend_factory(args.lp)
+    if be.k >= 5:
+        print("Error: at most 4 objectives are supported.", file=sys.stderr)
+        return 2
+    t0, c0 = time.monotonic(), time.process_time()
+    if args.split:
+        front = epp_front(be, dist, max(1, args.threads), args.split_normal)
+    else:
+        if args.threads > 1 and dist.rank == 0:
+            print("note: -t > 1 without --split runs one worker (bound-sharing protocol not re-hosted)", file=sys.stderr)
+        front = be.sequential_front()
+    wall, cpu = time.monotonic() - t0, time.process_time() - c0
+    if dist.rank == 0:
+        with open(out_path, "w") as fh:
+            fh.write(format_out(front, cpu, wall, int(be.ip_count()), "moip_b200"))
+    dist.barrier()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

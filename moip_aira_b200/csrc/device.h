@@ -1,0 +1,105 @@
+// Device-side views shared by the kernels (sm_100a) and the host driver.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/moip_b200.h"
+
+namespace moip {
+
+#define MOIP_CUDA(call)                                                                      \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      std::fprintf(stderr, "moip_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_), \
+                   __FILE__, __LINE__, #call);                                               \
+      return MOIP_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+// Model image in HBM (read-only for all kernels; ~nnz*12 + k*n*16 bytes, L1/L2 resident).
+struct DevModel {
+  int n, ms, k, m, ell_w, nnz;
+  double sgn;                 // +1 MIN, -1 MAX: kernels work on the min-form  min sgn*c x
+  double eta;                 // 0.98 / ||S||_2
+  double norm_row_bounds2;    // sum of squares of finite *unscaled* structural rhs
+  // scaled LP image
+  const double* ellT_val;     // [ell_w][n]  structural part of S^T, column-ELL
+  const int* ellT_row;        // [ell_w][n]
+  const int* s_ptr;           // [ms+1]      structural part of S, CSR
+  const int* s_col;           // [nnz]
+  const double* s_val;        // [nnz]
+  const double* D;            // [k][n]      dense scaled objective block (rows ms..m-1 of S)
+  const double* s_lo;         // [ms] scaled structural row bounds (+-inf)
+  const double* s_hi;
+  const double* dr;           // [m]
+  const double* dc;           // [n]
+  // exact integer image
+  const long long* ai_val;    // [nnz] (pattern s_ptr/s_col)
+  const long long* ri_lo;     // [ms]  LLONG_MIN = free
+  const long long* ri_hi;     // [ms]  LLONG_MAX = free
+  const long long* ci;        // [k][n]
+  const int* lbI;             // [n]
+  const int* ubI;             // [n]
+};
+
+// One batch of node LPs (K1).  All arrays are device pointers.
+struct LpBatch {
+  int B;
+  const int* cost_idx;        // [B]
+  const double* rhs;          // [B][k] objective-bound rows in the model's own sign (+-1e20 free)
+  const int* lb;              // [B][n] integer column bounds of the node
+  const int* ub;
+  const double* warm_x;       // [B][n] unscaled warm start or nullptr
+  const double* warm_y;       // [B][m]
+  double* out_x;              // [B][n] or nullptr
+  double* out_y;              // [B][m] or nullptr
+  double* primal_obj;         // [B] min-form objective of the last primal iterate
+  double* dual_bound;         // [B] best valid Lagrangian bound seen (min-form)
+  int* status;                // [B] MOIP_LP_*
+  int* iters;                 // [B]
+  int* branch_var;            // [B] most fractional column or -1
+  double* branch_val;         // [B] its (fractional) value
+  const int* skip;            // [B] nonzero: node already decided by K2, do not solve (or nullptr)
+  int cost_stride, rhs_stride;// 0 = all nodes share cost_idx[0] / rhs[0..k)
+  const double* cutoff;       // device scalar (min-form); node stops once bound >= *cutoff - cutoff_slack
+  int* work_counter;          // device int, zeroed before launch (dynamic node scheduling)
+};
+
+struct LpParams {
+  double eps;
+  int max_iter;
+  int check_every;
+  int fixed_iters;
+  int norm_every;             // restart criteria evaluated every this many iterations
+  double cutoff_slack;        // stop when bound >= cutoff - slack (integer objectives: 1 - 1e-6)
+};
+
+int launch_k1(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
+int launch_expand_masks(const DevModel& dm, int B, const uint32_t* masks, int mask_words, int* lb, int* ub,
+                        cudaStream_t st);
+
+// K3: one cached subproblem = one 64-byte record (ip: the k bounds it was solved under,
+// result: its lexicographic optimum, reference src/result.h:10-20)
+struct alignas(16) CacheRecord {
+  double ip[MOIP_MAX_OBJ];
+  int result[MOIP_MAX_OBJ];
+  int infeasible;
+  int pad[3];
+};
+static_assert(sizeof(CacheRecord) == 64, "cache record must be 64 bytes");
+struct DevCache {
+  int k, size;
+  const CacheRecord* rec;     // [size], insertion order
+};
+// searches up to two stores per query (infeasibles first, then solutions: reference
+// src/aira.cpp:816-823); first_match[q] = index in store `which[q]` (0/1) or -1
+int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queries, int sense, int* first_match,
+              int* which, cudaStream_t st);
+
+// K4
+int launch_k4(const DevModel& dm, int B, const int* x, const double* rhs, long long* obj_out,
+              unsigned char* feasible_out, cudaStream_t st);
+
+}  // namespace moip

@@ -1,0 +1,306 @@
+// Subproblem generator re-hosted on the C ABI: the sequential ("-t 1") and EPP ("--split") paths of
+// the reference's optimise<sense>() (reference src/aira.cpp:538-1884) and the EPP driver
+// (reference src/aira.cpp:1886-1990), written as an explicit state machine over the bound vector.
+// The inter-thread bound cells of the synergistic mode (src/aira.cpp:923-1086, :1111-1552) are out
+// of scope here.
+//
+// State per worker: rhs[k] (current bounds), hi_seen[]/lo_seen[] (the reference's max[]/min[]
+// trackers), misses (its infcnt), last_missed (inflast), level (depth_level), walking (onwalk).
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "solver.h"
+
+int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which);
+
+namespace moip {
+
+struct GenBackend {
+  virtual ~GenBackend() {}
+  virtual int solve(const int* perm, int n_obj, const double* rhs, int* result, int* status) = 0;
+  virtual int find(const double* rhs, int* hit, int* infeasible, int* result) = 0;
+  virtual int insert(const double* rhs, const int* result, int infeasible) = 0;
+};
+
+namespace {
+
+// `max[d]-1` / `min[d]+1` in the reference are int expressions whose trackers may sit at
+// (int)-CPX_INFBOUND = INT_MIN / (int)CPX_INFBOUND = INT_MAX; the front only comes out right when
+// the two's-complement wrap the reference gets in practice is reproduced.
+inline int wrap32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }
+
+}  // namespace
+
+int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* n_iter, int64_t* n_hit) {
+  const bool is_min = sense == MOIP_SENSE_MIN;
+  const double free_rhs = is_min ? kInf : -kInf;
+  const int* perm = w.perm;
+  const int n_obj = w.n_obj;
+  const bool split = w.split != 0;
+  const double split_start = w.split_start;
+  double split_stop = w.split_stop;
+  std::vector<double> rhs(k, free_rhs);
+  std::vector<int> res(k, 0), hi_seen(k, 0), lo_seen(k, 0);
+  int status = 0, rc;
+  const int last = perm[n_obj - 1];
+  if (split) rhs[last] = split_start;                                       // :607
+  if ((rc = be.solve(perm, n_obj, rhs.data(), res.data(), &status))) return rc;   // :614
+  const bool root_infeasible = status == MOIP_MIP_INFEASIBLE;
+  if ((rc = be.insert(rhs.data(), res.data(), root_infeasible ? 1 : 0))) return rc;   // :644-651
+  if (root_infeasible) return MOIP_OK;   // nothing lies inside these bounds (reference: trackers undefined)
+  if (split) split_stop += is_min ? -1.0 : 1.0;                             // :653-657
+  hi_seen = res; lo_seen = res;                                             // :693-697
+
+  auto tighten = [&](int d) {   // move the bound of objective d just past everything seen, reset its tracker
+    if (is_min) { rhs[d] = (double)wrap32((int64_t)hi_seen[d] - 1); hi_seen[d] = INT_MIN; }
+    else { rhs[d] = (double)wrap32((int64_t)lo_seen[d] + 1); lo_seen[d] = INT_MAX; }
+  };
+  // NB: the strip tests index rhs by position n_obj-1, not perm (src/aira.cpp:781, :882); EPP workers
+  // use the identity permutation so both agree.
+  auto crossed_stop = [&]() { return is_min ? rhs[n_obj - 1] < split_stop : rhs[n_obj - 1] > split_stop; };
+
+  for (int active = 1; active < n_obj; ++active) {                          // :723 objective_counter
+    const int objective = perm[active];
+    int level = 1, depth = perm[level];
+    bool walking = false, last_missed = false;
+    int misses = 0;
+    for (int jp = 1; jp < k; ++jp) rhs[perm[jp]] = free_rhs;                // :733-756
+    if (split) rhs[last] = split_start;                                     // :757-759
+    rhs[objective] = is_min ? (double)wrap32((int64_t)hi_seen[objective] - 1)
+                            : (double)wrap32((int64_t)lo_seen[objective] + 1);   // :761-777
+    if (split && crossed_stop()) break;                                     // :778-801
+    hi_seen[objective] = INT_MIN;                                           // :802-803
+    lo_seen[objective] = INT_MAX;
+    while (misses < active) {                                               // :804
+      int hit = 0, infeasible = 0;
+      if ((rc = be.find(rhs.data(), &hit, &infeasible, res.data()))) return rc;   // :816-827
+      if (n_iter) ++*n_iter;
+      if (hit) { if (n_hit) ++*n_hit; }
+      else {
+        if ((rc = be.solve(perm, n_obj, rhs.data(), res.data(), &status))) return rc;   // :835
+        infeasible = (status == MOIP_MIP_INFEASIBLE || status == MOIP_MIP_INFORUNBD) ? 1 : 0;
+        if ((rc = be.insert(rhs.data(), res.data(), infeasible))) return rc;            // :842-850
+      }
+      if (split) {                                                          // :877-922
+        if (!infeasible) {
+          if (misses == n_obj - 2 && crossed_stop()) infeasible = 1;
+          for (int j = 0; j < k; ++j) { if (res[j] > hi_seen[j]) hi_seen[j] = res[j]; if (res[j] < lo_seen[j]) lo_seen[j] = res[j]; }
+        }
+      } else if (!infeasible) {                                             // :1087-1107
+        for (int j = 0; j < k; ++j) { if (res[j] > hi_seen[j]) hi_seen[j] = res[j]; if (res[j] < lo_seen[j]) lo_seen[j] = res[j]; }
+      }
+      if (infeasible) { ++misses; last_missed = true; } else { misses = 0; last_missed = false; }
+      // next bound vector (:1575-1832)
+      if (infeasible && misses == active - 1) {
+        for (int j = 0; j < k; ++j) rhs[j] = free_rhs;                      // :1586-1599
+        if (split) rhs[n_obj - 1] = split_start;                            // :1649-1651
+        tighten(objective);                                                 // :1655-1673
+        level = 1; depth = perm[level]; walking = false;
+      } else if (last_missed && misses != active) {
+        rhs[depth] = free_rhs;                                              // :1722-1728
+        depth = perm[++level];                                              // :1730-1731
+        tighten(depth);                                                     // :1758-1760 / :1778-1780
+        walking = true;
+      } else if (!walking && misses != 1) {
+        tighten(depth);                                                     // :1797-1798 / :1806-1807
+      } else if (walking && misses != 1) {
+        level = 1; depth = perm[level];
+        tighten(depth);                                                     // :1810-1831
+        walking = false;
+      }
+    }
+  }
+  return MOIP_OK;
+}
+
+namespace {
+
+// GPU backend: solve = lexicographic B&B on the device, find = K3 over (infeasibles, solutions)
+struct GpuBackend : GenBackend {
+  moip_ctx* c;
+  moip_cache* infeasibles;
+  moip_cache* sols;
+  int sense;
+  int solve(const int* perm, int n_obj, const double* rhs, int* result, int* status) override {
+    return c->lex_solve(perm, n_obj, rhs, result, status);
+  }
+  int find(const double* rhs, int* hit, int* infeasible, int* result) override {
+    int idx = -1, which = -1;
+    if (infeasibles->host.empty() && sols->host.empty()) { *hit = 0; return MOIP_OK; }
+    int rc = cache_find2(c, infeasibles, sols, 1, rhs, sense, &idx, &which);
+    if (rc) return rc;
+    *hit = idx >= 0;
+    if (idx >= 0) {
+      const CacheRecord& r = (which == 0 ? infeasibles : sols)->host[idx];
+      *infeasible = r.infeasible;
+      for (int j = 0; j < c->dm.k; ++j) result[j] = r.result[j];
+    }
+    return MOIP_OK;
+  }
+  int insert(const double* rhs, const int* result, int infeasible) override {
+    return moip_cache_insert(infeasible ? infeasibles : sols, rhs, result, infeasible);
+  }
+};
+
+struct CallbackBackend : GenBackend {
+  moip_solve_fn solve_fn;
+  moip_find_cb find_fn;
+  moip_insert_cb insert_fn;
+  void* user;
+  int solve(const int* perm, int n_obj, const double* rhs, int* result, int* status) override {
+    return solve_fn(user, perm, n_obj, rhs, result, status);
+  }
+  int find(const double* rhs, int* hit, int* infeasible, int* result) override {
+    *hit = find_fn(user, rhs, infeasible, result);
+    return *hit < 0 ? MOIP_ERR_ARG : MOIP_OK;
+  }
+  int insert(const double* rhs, const int* result, int infeasible) override {
+    return insert_fn(user, rhs, result, infeasible);
+  }
+};
+
+}  // namespace
+}  // namespace moip
+
+using namespace moip;
+
+extern "C" int moip_optimise(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles) {
+  if (!c || !w || !all || !infeasibles || w->n_obj < 1 || w->n_obj > c->dm.k) return MOIP_ERR_ARG;
+  const int sense = c->model->M.sense;
+  moip_cache* local = nullptr;                       // `Solutions s(p.objcnt)` (src/aira.cpp:587)
+  int rc = moip_cache_create(c, &local);
+  if (rc) return rc;
+  GpuBackend be;
+  be.c = c; be.infeasibles = infeasibles; be.sols = w->split ? all : local; be.sense = sense;
+  rc = run_worker(be, c->dm.k, sense, *w, nullptr, nullptr);
+  if (!rc) {
+    moip_cache_sort_unique(local, nullptr, 0);       // :1877
+    rc = moip_cache_merge(all, local);               // :1879
+  }
+  moip_cache_destroy(local);
+  return rc;
+}
+
+extern "C" int moip_optimise_with(int k, int sense, const moip_worker* w, moip_solve_fn solve, moip_find_cb find,
+                                  moip_insert_cb insert, void* user, int64_t* n_iterations, int64_t* n_hits) {
+  if (!w || !solve || !find || !insert || k < 1 || k > MOIP_MAX_OBJ) return MOIP_ERR_ARG;
+  CallbackBackend be;
+  be.solve_fn = solve; be.find_fn = find; be.insert_fn = insert; be.user = user;
+  if (n_iterations) *n_iterations = 0;
+  if (n_hits) *n_hits = 0;
+  return run_worker(be, k, sense, *w, n_iterations, n_hits);
+}
+
+extern "C" int moip_split_strips(int sense, int biggest, int smallest, int num_threads, int split_normal,
+                                 double* start_stop) {
+  // the quantile table is data of the reference (src/aira.cpp:55-69)
+  static const double nv[13][13] = {
+      {0}, {0, 1}, {0, 0.5, 1}, {0, 0.356, 0.644, 1}, {0, 0.275, 0.5, 0.725, 1},
+      {0, 0.219, 0.416, 0.584, 0.781, 1}, {0, 0.178, 0.256, 0.5, 0.644, 0.822, 1},
+      {0, 0.144, 0.311, 0.44, 0.56, 0.689, 0.856, 1}, {0, 0.117, 0.275, 0.394, 0.5, 0.606, 0.725, 0.883, 1},
+      {0, 0.093, 0.245, 0.356, 0.453, 0.547, 0.644, 0.755, 0.907, 1},
+      {0, 0.073, 0.219, 0.325, 0.416, 0.5, 0.584, 0.675, 0.781, 0.927, 1},
+      {0, 0.055, 0.197, 0.298, 0.384, 0.462, 0.538, 0.616, 0.702, 0.803, 0.945, 1},
+      {0, 0.039, 0.178, 0.275, 0.356, 0.430, 0.5, 0.570, 0.644, 0.725, 0.822, 0.961, 1}};
+  if (!start_stop || num_threads < 1) return MOIP_ERR_ARG;
+  if (split_normal && num_threads > 12) return MOIP_ERR_ARG;               // :199-203
+  const bool is_min = sense == MOIP_SENSE_MIN;
+  const double start_point = is_min ? (double)biggest : (double)smallest;  // :1888-1894
+  const double stop_point = is_min ? (double)smallest : (double)biggest;
+  double cur = start_point;
+  const double step = (stop_point - start_point) / num_threads;           // :1897
+  for (int t = 0; t < num_threads; ++t) {
+    if (split_normal) {                                                    // :1900-1911
+      double a, b;
+      if (is_min) { const double gap = start_point - stop_point; b = nv[num_threads][t] * gap + stop_point; a = nv[num_threads][t + 1] * gap + stop_point; }
+      else { const double gap = stop_point - start_point; a = nv[num_threads][t] * gap + start_point; b = nv[num_threads][t + 1] * gap + start_point; }
+      start_stop[2 * t] = a; start_stop[2 * t + 1] = b;
+    } else {                                                               // :1913-1915
+      start_stop[2 * t] = cur; start_stop[2 * t + 1] = cur + step;
+      cur += step;
+    }
+  }
+  return MOIP_OK;
+}
+
+namespace {
+
+// split_setup / split_optimise (src/aira.cpp:1886-1990) with the strips of one level solved one
+// after another on this context, sharing `here` and `infeasibles` like the reference's threads do.
+int epp_level(moip_ctx* c, int n_obj, int num_threads, int split_normal, std::vector<std::vector<int>>& sols) {
+  const int k = c->dm.k, sense = c->model->M.sense;
+  const bool is_min = sense == MOIP_SENSE_MIN;
+  std::vector<double> free_rhs(k, is_min ? kInf : -kInf);
+  std::vector<int> res(k, 0);
+  int st = 0, rc;
+  if (n_obj == 1) {                                                        // :1946-1949
+    if ((rc = c->get_limit(0, sense, free_rhs.data(), res.data(), &st))) return rc;
+    if (st != MOIP_MIP_INFEASIBLE) sols.push_back(res);
+    return MOIP_OK;
+  }
+  std::vector<std::vector<int>> lower;
+  if ((rc = epp_level(c, n_obj - 1, num_threads, split_normal, lower))) return rc;
+  if (lower.empty()) return MOIP_OK;                                       // infeasible model
+  if ((rc = c->get_limit(n_obj - 1, sense, free_rhs.data(), res.data(), &st))) return rc;   // :1959 / :1971
+  if (st == MOIP_MIP_INFEASIBLE) return MOIP_OK;
+  int biggest, smallest;
+  if (is_min) {                                                            // :1958-1969
+    smallest = res[n_obj - 1]; biggest = INT_MIN;
+    for (auto& s : lower) biggest = std::max(biggest, s[n_obj - 1]);
+    if (biggest == smallest) biggest = INT_MAX;
+  } else {                                                                 // :1970-1982
+    biggest = res[n_obj - 1]; smallest = INT_MAX;
+    for (auto& s : lower) smallest = std::min(smallest, s[n_obj - 1]);
+    if (biggest == smallest) smallest = INT_MIN;
+  }
+  std::vector<double> ss(2 * (size_t)num_threads);
+  if ((rc = moip_split_strips(sense, biggest, smallest, num_threads, split_normal, ss.data()))) return rc;
+  moip_cache *here = nullptr, *infeasibles = nullptr;
+  if ((rc = moip_cache_create(c, &here))) return rc;
+  if ((rc = moip_cache_create(c, &infeasibles))) { moip_cache_destroy(here); return rc; }
+  for (int t = 0; t < num_threads && !rc; ++t) {                           // :1899-1933
+    moip_worker w{};
+    w.id = t; w.n_obj = n_obj; w.split = 1;
+    for (int i = 0; i < k; ++i) w.perm[i] = i;                             // thread.cpp:124-133
+    w.split_start = ss[2 * t]; w.split_stop = ss[2 * t + 1];
+    rc = moip_optimise(c, &w, here, infeasibles);
+  }
+  if (!rc)
+    for (auto& r : here->host) if (!r.infeasible) sols.emplace_back(r.result, r.result + k);   // :1934-1942
+  moip_cache_destroy(here);
+  moip_cache_destroy(infeasibles);
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int moip_pareto_front(moip_ctx* c, int split, int num_threads, int split_normal, int* rows_out, int cap,
+                                 int* n_rows) {
+  if (!c || !n_rows) return MOIP_ERR_ARG;
+  const int k = c->dm.k;
+  moip_cache* all = nullptr;
+  int rc = moip_cache_create(c, &all);
+  if (rc) return rc;
+  if (split) {                                                             // src/aira.cpp:269-276
+    if (num_threads < 1) num_threads = 1;
+    std::vector<std::vector<int>> sols;
+    rc = epp_level(c, k, num_threads, split_normal, sols);
+    std::vector<double> zero(k, 0.0);
+    for (auto& s : sols) moip_cache_insert(all, zero.data(), s.data(), 0);
+  } else {                                                                 // src/aira.cpp:277-308 with -t 1
+    moip_cache* infeasibles = nullptr;
+    rc = moip_cache_create(c, &infeasibles);
+    if (!rc) {
+      moip_worker w{};
+      w.id = 0; w.n_obj = k; w.split = 0;
+      for (int i = 0; i < k; ++i) w.perm[i] = i;
+      rc = moip_optimise(c, &w, all, infeasibles);
+      moip_cache_destroy(infeasibles);
+    }
+  }
+  if (!rc) *n_rows = moip_cache_sort_unique(all, rows_out, cap);           // src/aira.cpp:336-346
+  moip_cache_destroy(all);
+  return rc;
+}

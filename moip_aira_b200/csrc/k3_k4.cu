@@ -1,0 +1,135 @@
+// K3 -- batched reuse/dominance scan (Solutions::find, reference src/solutions.cpp:11-81)
+// K4 -- exact int64 verification of integer points (the round()/Sum c*x of reference
+//       src/aira.cpp:517-530, done exactly instead of in fp64).
+#include <climits>
+
+#include "device.h"
+
+namespace moip {
+namespace {
+
+// One CTA per query; records (64-byte AoS, four 16-byte loads per thread) are visited in
+// insertion order in chunks of NT so the first match (lowest index) is found with an early exit.
+template <int NT>
+__global__ void __launch_bounds__(NT) k3_scan_kernel(const DevCache c0, const DevCache c1, int Q, const double* queries,
+                                                     int sense, int* first_match, int* which) {
+  __shared__ int s_best;
+  const int tid = threadIdx.x;
+  const int k = c0.k;
+  for (int q = blockIdx.x; q < Q; q += gridDim.x) {
+    double ip[MOIP_MAX_OBJ];
+#pragma unroll
+    for (int i = 0; i < MOIP_MAX_OBJ; ++i) ip[i] = (i < k) ? queries[(size_t)q * k + i] : 0.0;
+    int found = -1, found_in = -1;
+    for (int st = 0; st < 2 && found < 0; ++st) {
+      const DevCache& c = st == 0 ? c0 : c1;
+      if (c.size <= 0) continue;
+      if (tid == 0) s_best = INT_MAX;
+      __syncthreads();
+      for (int base = 0; base < c.size; base += NT) {
+        const int r = base + tid;
+        bool ok = r < c.size;
+        if (ok) {
+          const int4* p = reinterpret_cast<const int4*>(c.rec + r);
+          const int4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+          double rip[4];
+          rip[0] = __hiloint2double(v0.y, v0.x); rip[1] = __hiloint2double(v0.w, v0.z);
+          rip[2] = __hiloint2double(v1.y, v1.x); rip[3] = __hiloint2double(v1.w, v1.z);
+          const int res[4] = {v2.x, v2.y, v2.z, v2.w};
+          const bool inf = v3.x != 0;
+#pragma unroll
+          for (int i = 0; i < MOIP_MAX_OBJ; ++i) {
+            if (i < k) {
+              if (sense == MOIP_SENSE_MIN) {
+                if (rip[i] < ip[i]) ok = false;                         // t1 (src/solutions.cpp:20)
+                if (!inf && (double)res[i] > ip[i]) ok = false;         // t3 (:25-30)
+              } else {
+                if (rip[i] > ip[i]) ok = false;                         // t1 (:35)
+                if (!inf && (double)res[i] < ip[i]) ok = false;         // t3 (:40-45)
+              }
+            }
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (bal && (tid & 31) == 0) atomicMin(&s_best, base + (tid & ~31) + (__ffs(bal) - 1));
+        __syncthreads();
+        const bool hit = s_best != INT_MAX;   // uniform: read between the two barriers
+        __syncthreads();
+        if (hit) break;
+      }
+      if (s_best != INT_MAX) { found = s_best; found_in = st; }
+      __syncthreads();
+    }
+    if (tid == 0) { first_match[q] = found; if (which) which[q] = found_in; }
+  }
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per point: column bounds, structural rows (CSR, int64) and the k objectives.
+__global__ void __launch_bounds__(128) k4_verify_kernel(const DevModel dm, int B, const int* x, const double* rhs,
+                                                        long long* obj_out, unsigned char* feasible_out) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int p = wglobal; p < B; p += nwarps) {
+    const int* xp = x + (size_t)p * dm.n;
+    int bad = 0;
+    long long obj[MOIP_MAX_OBJ] = {0, 0, 0, 0};
+    for (int j = lane; j < dm.n; j += 32) {
+      const int v = xp[j];
+      if (v < dm.lbI[j] || v > dm.ubI[j]) bad = 1;
+#pragma unroll
+      for (int o = 0; o < MOIP_MAX_OBJ; ++o)
+        if (o < dm.k) obj[o] += dm.ci[(size_t)o * dm.n + j] * (long long)v;
+    }
+#pragma unroll
+    for (int o = 0; o < MOIP_MAX_OBJ; ++o) obj[o] = warp_sum_ll(obj[o]);
+    for (int i = 0; i < dm.ms; ++i) {
+      long long a = 0;
+      for (int e = dm.s_ptr[i] + lane; e < dm.s_ptr[i + 1]; e += 32) a += dm.ai_val[e] * (long long)xp[dm.s_col[e]];
+      a = warp_sum_ll(a);
+      if (a < dm.ri_lo[i] || a > dm.ri_hi[i]) bad = 1;
+    }
+    if (rhs) {
+      for (int o = 0; o < dm.k; ++o) {
+        const double r = rhs[(size_t)p * dm.k + o];
+        if (fabs(r) < 1e19) {
+          if (dm.sgn > 0 ? ((double)obj[o] > r) : ((double)obj[o] < r)) bad = 1;
+        }
+      }
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+      feasible_out[p] = bad ? 0 : 1;
+      for (int o = 0; o < dm.k; ++o) obj_out[(size_t)p * dm.k + o] = obj[o];
+    }
+  }
+}
+
+}  // namespace
+
+int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queries, int sense, int* first_match,
+              int* which, cudaStream_t st) {
+  if (Q <= 0) return MOIP_OK;
+  int grid = Q < 148 * 16 ? Q : 148 * 16;
+  k3_scan_kernel<128><<<grid, 128, 0, st>>>(c0, c1, Q, queries, sense, first_match, which);
+  MOIP_CUDA(cudaGetLastError());
+  return MOIP_OK;
+}
+
+int launch_k4(const DevModel& dm, int B, const int* x, const double* rhs, long long* obj_out,
+              unsigned char* feasible_out, cudaStream_t st) {
+  if (B <= 0) return MOIP_OK;
+  int blocks = (B + 3) / 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k4_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, x, rhs, obj_out, feasible_out);
+  MOIP_CUDA(cudaGetLastError());
+  return MOIP_OK;
+}
+
+}  // namespace moip

@@ -1,0 +1,59 @@
+// Host-side model: what the reference keeps in Problem + the opaque CPXLPptr
+// (reference src/problem.h:11-21, src/env.h:6-10), rebuilt without CPLEX, plus the
+// derived images the kernels need (exact integer image, scaled LP image).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace moip {
+
+constexpr double kInf = 1.0e20;  // CPX_INFBOUND (reference src/problem.cpp:126)
+
+struct Model {
+  // ---- as read from the file ------------------------------------------------------------
+  std::string path;
+  int n = 0, ms = 0, k = 0;
+  int sense = 0;                       // 0 MIN, 1 MAX (reference src/sense.h)
+  std::vector<std::string> names;      // column names, order of first appearance
+  // structural rows in CSR (file order)
+  std::vector<int> a_ptr, a_col;
+  std::vector<double> a_val;
+  std::vector<char> row_sense;         // 'L','G','E'
+  std::vector<double> rhs;             // ms
+  std::vector<double> objcoef;         // k*n dense, Problem::objcoef
+  std::vector<double> lb, ub;          // column bounds (kInf = none)
+  std::vector<uint8_t> is_int;
+
+  // ---- exact integer image (K2/K4) -------------------------------------------------------
+  // row i:  lo_i <= sum a_ij x_j <= hi_i  with int64 data; columns lbI..ubI (int32)
+  std::vector<int64_t> ai_val;         // same pattern as a_ptr/a_col
+  std::vector<int64_t> ri_lo, ri_hi;   // ms (INT64_MIN/MAX = free side)
+  std::vector<int64_t> ci;             // k*n objective coefficients
+  std::vector<int32_t> lbI, ubI;       // implied-finite integer bounds
+  bool all_binary = false;
+  bool int_infeasible = false;         // an equality row with non-integral rhs etc.
+
+  // ---- scaled LP image (K1): K = [A ; sgn*C], S = Dr K Dc ---------------------------------
+  int m = 0;                           // ms + k
+  std::vector<double> dr, dc;          // row / column scalings (x = dc*xs, y = dr*ys)
+  // structural part of S^T in column-ELL: entry e of column j at [e*n + j]
+  int ell_w = 0;
+  std::vector<double> ellT_val;
+  std::vector<int> ellT_row;
+  // structural part of S in CSR
+  std::vector<double> s_val;           // pattern = a_ptr/a_col
+  // dense objective block D = Dr[ms..] * sgn*C * Dc  (k*n)
+  std::vector<double> D;
+  std::vector<double> s_lo, s_hi;      // scaled structural row bounds (+-inf as +-HUGE_VAL)
+  double eta = 0;                      // 0.99 / ||S||_2
+  double norm_row_bounds2 = 0;         // sum of squares of finite scaled structural bounds
+};
+
+// Loads .lp / .mop (dispatch on extension like reference src/problem.cpp:16-26).
+// Returns 0 on success; on failure fills err.
+int load_model(const std::string& path, Model& out, std::string& err);
+// Builds integer + scaled images; called by load_model.
+int finalize_model(Model& m, std::string& err);
+
+}  // namespace moip

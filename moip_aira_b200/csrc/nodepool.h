@@ -1,0 +1,27 @@
+// Node pool shared between the host B&B driver and the K2 kernels.
+#pragma once
+#include "device.h"
+
+namespace moip {
+
+// Pool slot s: integer column bounds + warm start of one open B&B node (HBM resident).
+struct PoolView {
+  int* lb;      // [slots][n]
+  int* ub;      // [slots][n]
+  double* wx;   // [slots][n]  unscaled LP primal iterate of the parent / of the node itself
+  double* wy;   // [slots][m]
+};
+
+struct BranchOp {
+  int parent, child, var, new_lb, new_ub;
+};
+
+int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const int* ids, const long long* obj_lo,
+                        const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st);
+int launch_k2_branch(const DevModel& dm, const PoolView& pool, int C, const BranchOp* ops, cudaStream_t st);
+int launch_k2_gather(const DevModel& dm, const PoolView& pool, int B, const int* ids, int* lb, int* ub, double* wx,
+                     double* wy, cudaStream_t st);
+int launch_k2_scatter_round(const DevModel& dm, const PoolView& pool, int B, const int* ids, const double* x,
+                            const double* y, int* xr, cudaStream_t st);
+
+}  // namespace moip

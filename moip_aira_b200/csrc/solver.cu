@@ -1,0 +1,696 @@
+// Host driver: contexts, the batched node-LP API, the solution cache, int64 verification and the
+// branch-and-bound + lexicographic chain that replace the bodies of solve() / get_limit()
+// (reference src/aira.cpp:452-536, :367-450).  Host C++ keeps the control; all arithmetic on
+// model data runs in the kernels of k1_pdhg.cu / k2_nodepool.cu / k3_k4.cu.
+#include "solver.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+using namespace moip;
+
+namespace {
+
+template <class T>
+int upload(moip_ctx* c, const std::vector<T>& v, const T** out) {
+  T* p = nullptr;
+  size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+  MOIP_CUDA(cudaMalloc(&p, bytes));
+  if (!v.empty()) MOIP_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  c->model_allocs.push_back(p);
+  *out = p;
+  return MOIP_OK;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return s ? std::atoi(s) : dflt;
+}
+double env_double(const char* name, double dflt) {
+  const char* s = std::getenv(name);
+  return s ? std::atof(s) : dflt;
+}
+
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ context
+extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx** out) {
+  if (!m || !out) return MOIP_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    std::fprintf(stderr, "moip_b200: no CUDA device available (this library has no CPU fallback)\n");
+    return MOIP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return MOIP_ERR_ARG;
+  MOIP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MOIP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    std::fprintf(stderr, "moip_b200: device %d is sm_%d%d; kernels are built for sm_100a only\n", device, prop.major, prop.minor);
+    return MOIP_ERR_CUDA;
+  }
+  moip_ctx* c = new moip_ctx();
+  c->model = m;
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  c->num_sms = prop.multiProcessorCount;
+  const Model& M = m->M;
+  DevModel& d = c->dm;
+  d.n = M.n; d.ms = M.ms; d.k = M.k; d.m = M.m; d.ell_w = M.ell_w; d.nnz = (int)M.a_val.size();
+  d.sgn = M.sense == 0 ? 1.0 : -1.0;
+  d.eta = M.eta;
+  double nb2 = 0;
+  for (int i = 0; i < M.ms; ++i) nb2 += M.rhs[i] * M.rhs[i];
+  d.norm_row_bounds2 = nb2;
+  int rc = 0;
+  std::vector<long long> ai(M.ai_val.begin(), M.ai_val.end()), rlo(M.ri_lo.begin(), M.ri_lo.end()),
+      rhi(M.ri_hi.begin(), M.ri_hi.end()), ci(M.ci.begin(), M.ci.end());
+  for (auto& v : rlo) if (v == INT64_MIN) v = LLONG_MIN;
+  for (auto& v : rhi) if (v == INT64_MAX) v = LLONG_MAX;
+  rc |= upload(c, M.ellT_val, &d.ellT_val);
+  rc |= upload(c, M.ellT_row, &d.ellT_row);
+  rc |= upload(c, M.a_ptr, &d.s_ptr);
+  rc |= upload(c, M.a_col, &d.s_col);
+  rc |= upload(c, M.s_val, &d.s_val);
+  rc |= upload(c, M.D, &d.D);
+  rc |= upload(c, M.s_lo, &d.s_lo);
+  rc |= upload(c, M.s_hi, &d.s_hi);
+  rc |= upload(c, M.dr, &d.dr);
+  rc |= upload(c, M.dc, &d.dc);
+  rc |= upload(c, ai, &d.ai_val);
+  rc |= upload(c, rlo, &d.ri_lo);
+  rc |= upload(c, rhi, &d.ri_hi);
+  rc |= upload(c, ci, &d.ci);
+  rc |= upload(c, M.lbI, &d.lbI);
+  rc |= upload(c, M.ubI, &d.ubI);
+  if (rc) { moip_ctx_destroy(c); return MOIP_ERR_CUDA; }
+  c->root_x.assign(M.k, {});
+  c->root_y.assign(M.k, {});
+  c->bb_batch = env_int("MOIP_BB_BATCH", 0);
+  c->bb_max_iter = env_int("MOIP_BB_MAX_ITER", 3000);
+  c->bb_eps = env_double("MOIP_BB_EPS", 1e-5);
+  c->bb_check = env_int("MOIP_BB_CHECK", 32);
+  c->norm_every = env_int("MOIP_NORM_EVERY", 1);
+  *out = c;
+  return MOIP_OK;
+}
+
+extern "C" void moip_ctx_destroy(moip_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (void* p : c->model_allocs) cudaFree(p);
+  c->b_cost.release(); c->b_lb.release(); c->b_ub.release(); c->b_status.release(); c->b_iters.release();
+  c->b_branch.release(); c->b_counter.release(); c->b_rhs.release(); c->b_pobj.release(); c->b_dbound.release();
+  c->b_x.release(); c->b_cutoff.release(); c->b_masks.release();
+  c->q_ip.release(); c->q_out.release(); c->q_which.release(); c->h_q.release();
+  c->v_x.release(); c->v_rhs.release(); c->v_obj.release(); c->v_feas.release();
+  c->p_lb.release(); c->p_ub.release(); c->p_wx.release(); c->p_wy.release();
+  c->r_ids.release(); c->r_flag.release(); c->r_lb.release(); c->r_ub.release(); c->r_status.release();
+  c->r_iters.release(); c->r_branch.release(); c->r_xr.release(); c->r_counter.release();
+  c->r_wx.release(); c->r_wy.release(); c->r_x.release(); c->r_y.release(); c->r_pobj.release();
+  c->r_dbound.release(); c->r_bval.release(); c->r_rhs.release(); c->r_cutoff.release();
+  c->r_leaf.release(); c->r_olo.release(); c->r_ohi.release(); c->r_cobj.release(); c->r_cfeas.release();
+  c->r_ops.release(); c->h_round.release();
+  delete c;
+}
+
+extern "C" int moip_ctx_stats(const moip_ctx* c, moip_stats* out) {
+  if (!c || !out) return MOIP_ERR_ARG;
+  *out = c->stats;
+  return MOIP_OK;
+}
+extern "C" int moip_ctx_reset_stats(moip_ctx* c) {
+  if (!c) return MOIP_ERR_ARG;
+  c->stats = moip_stats{};
+  return MOIP_OK;
+}
+
+// ------------------------------------------------------------------------------------ K1 batch API
+extern "C" void moip_lp_default_params(moip_lp_params* p) {
+  if (!p) return;
+  p->eps = 1e-8;
+  p->max_iter = 100000;
+  p->check_every = 32;
+  p->fixed_iters = 0;
+  p->cutoff = MOIP_INFBOUND;
+}
+
+extern "C" int moip_lp_batch_upload(moip_ctx* c, int B, const int* cost_idx, const double* rhs, const uint32_t* fix_masks) {
+  if (!c || B < 0 || (B > 0 && (!cost_idx || !rhs))) return MOIP_ERR_ARG;
+  MOIP_CUDA(cudaSetDevice(c->device));
+  const DevModel& d = c->dm;
+  const int words = (d.n + 15) / 16;
+  for (int b = 0; b < B; ++b)
+    if (cost_idx[b] < 0 || cost_idx[b] >= d.k) return MOIP_ERR_ARG;
+  int rc = 0;
+  rc |= c->b_cost.ensure(B); rc |= c->b_rhs.ensure((size_t)B * d.k); rc |= c->b_masks.ensure((size_t)B * words);
+  rc |= c->b_lb.ensure((size_t)B * d.n); rc |= c->b_ub.ensure((size_t)B * d.n);
+  rc |= c->b_status.ensure(B); rc |= c->b_iters.ensure(B); rc |= c->b_branch.ensure(B);
+  rc |= c->b_pobj.ensure(B); rc |= c->b_dbound.ensure(B); rc |= c->b_x.ensure((size_t)B * d.n);
+  rc |= c->b_counter.ensure(1); rc |= c->b_cutoff.ensure(1);
+  if (rc) return MOIP_ERR_CUDA;
+  c->batch_B = B;
+  if (B == 0) return MOIP_OK;
+  MOIP_CUDA(cudaMemcpyAsync(c->b_cost.p, cost_idx, sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
+  MOIP_CUDA(cudaMemcpyAsync(c->b_rhs.p, rhs, sizeof(double) * B * d.k, cudaMemcpyHostToDevice, c->stream));
+  if (fix_masks)
+    MOIP_CUDA(cudaMemcpyAsync(c->b_masks.p, fix_masks, sizeof(uint32_t) * B * words, cudaMemcpyHostToDevice, c->stream));
+  rc = launch_expand_masks(d, B, fix_masks ? c->b_masks.p : nullptr, words, c->b_lb.p, c->b_ub.p, c->stream);
+  c->stats.kernel_launches += 1;
+  return rc;
+}
+
+extern "C" int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params) {
+  if (!c) return MOIP_ERR_ARG;
+  MOIP_CUDA(cudaSetDevice(c->device));
+  if (c->batch_B == 0) return MOIP_OK;
+  moip_lp_params dp;
+  moip_lp_default_params(&dp);
+  if (params) dp = *params;
+  const DevModel& d = c->dm;
+  // public cutoff is in the model's sense; kernels use the min-form
+  double cut = std::fabs(dp.cutoff) >= 1e19 ? HUGE_VAL : d.sgn * dp.cutoff;
+  MOIP_CUDA(cudaMemcpyAsync(c->b_cutoff.p, &cut, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  LpBatch b{};
+  b.B = c->batch_B;
+  b.cost_idx = c->b_cost.p; b.rhs = c->b_rhs.p; b.lb = c->b_lb.p; b.ub = c->b_ub.p;
+  b.warm_x = nullptr; b.warm_y = nullptr; b.out_x = c->b_x.p; b.out_y = nullptr;
+  b.primal_obj = c->b_pobj.p; b.dual_bound = c->b_dbound.p; b.status = c->b_status.p; b.iters = c->b_iters.p;
+  b.branch_var = c->b_branch.p; b.branch_val = nullptr; b.skip = nullptr;
+  b.cost_stride = 1; b.rhs_stride = d.k;
+  b.cutoff = c->b_cutoff.p; b.work_counter = c->b_counter.p;
+  LpParams p{};
+  p.eps = dp.eps; p.max_iter = dp.max_iter; p.check_every = dp.check_every > 0 ? dp.check_every : 32;
+  p.fixed_iters = dp.fixed_iters; p.norm_every = c->norm_every > 0 ? c->norm_every : 1;
+  p.cutoff_slack = 0.0;
+  c->stats.kernel_launches += 1;
+  c->stats.node_lps += b.B;
+  return launch_k1(d, b, p, c->num_sms, c->stream);
+}
+
+extern "C" int moip_lp_batch_download(moip_ctx* c, double* primal_obj, double* dual_bound, int* status, int* iters,
+                                      double* x_out) {
+  if (!c) return MOIP_ERR_ARG;
+  MOIP_CUDA(cudaSetDevice(c->device));
+  const int B = c->batch_B;
+  const DevModel& d = c->dm;
+  if (B > 0) {
+    if (primal_obj) MOIP_CUDA(cudaMemcpyAsync(primal_obj, c->b_pobj.p, sizeof(double) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (dual_bound) MOIP_CUDA(cudaMemcpyAsync(dual_bound, c->b_dbound.p, sizeof(double) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (status) MOIP_CUDA(cudaMemcpyAsync(status, c->b_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (iters) MOIP_CUDA(cudaMemcpyAsync(iters, c->b_iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+    if (x_out) MOIP_CUDA(cudaMemcpyAsync(x_out, c->b_x.p, sizeof(double) * B * d.n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  MOIP_CUDA(cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < B; ++b) {
+    if (primal_obj) primal_obj[b] *= d.sgn;
+    if (dual_bound) dual_bound[b] *= d.sgn;
+    if (iters) c->stats.lp_iterations += iters[b];
+  }
+  return MOIP_OK;
+}
+
+extern "C" int moip_lp_batch_solve(moip_ctx* c, int B, const int* cost_idx, const double* rhs, const uint32_t* fix_masks,
+                                   const moip_lp_params* params, double* primal_obj, double* dual_bound, int* status,
+                                   int* iters, double* x_out) {
+  int rc = moip_lp_batch_upload(c, B, cost_idx, rhs, fix_masks);
+  if (rc) return rc;
+  rc = moip_lp_batch_run(c, params);
+  if (rc) return rc;
+  return moip_lp_batch_download(c, primal_obj, dual_bound, status, iters, x_out);
+}
+
+// ------------------------------------------------------------------------------------ K3 cache
+int moip_cache::sync_to_device() {
+  if (synced == host.size()) return MOIP_OK;
+  MOIP_CUDA(cudaSetDevice(ctx->device));
+  if (dev.ensure(host.size(), true, ctx->stream)) return MOIP_ERR_CUDA;
+  MOIP_CUDA(cudaMemcpyAsync(dev.p + synced, host.data() + synced, sizeof(CacheRecord) * (host.size() - synced),
+                            cudaMemcpyHostToDevice, ctx->stream));
+  // host.data() may be reallocated by a later insert: finish the copy before returning
+  MOIP_CUDA(cudaStreamSynchronize(ctx->stream));
+  synced = host.size();
+  return MOIP_OK;
+}
+DevCache moip_cache::view() const {
+  DevCache v;
+  v.k = k; v.size = (int)synced; v.rec = dev.p;
+  return v;
+}
+
+extern "C" int moip_cache_create(moip_ctx* c, moip_cache** out) {
+  if (!c || !out) return MOIP_ERR_ARG;
+  moip_cache* s = new moip_cache();
+  s->ctx = c; s->k = c->dm.k;
+  *out = s;
+  return MOIP_OK;
+}
+extern "C" void moip_cache_destroy(moip_cache* s) {
+  if (!s) return;
+  cudaSetDevice(s->ctx->device);
+  s->dev.release();
+  delete s;
+}
+extern "C" int moip_cache_insert(moip_cache* s, const double* ip, const int* result, int infeasible) {
+  if (!s || !ip || (!infeasible && !result)) return MOIP_ERR_ARG;
+  CacheRecord r{};
+  for (int i = 0; i < s->k; ++i) { r.ip[i] = ip[i]; r.result[i] = (infeasible || !result) ? 0 : result[i]; }
+  r.infeasible = infeasible ? 1 : 0;
+  s->host.push_back(r);
+  return MOIP_OK;
+}
+extern "C" int moip_cache_size(const moip_cache* s) { return s ? (int)s->host.size() : -1; }
+
+// shared by the public batch call and the generator (two stores, one launch, one sync)
+int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which) {
+  MOIP_CUDA(cudaSetDevice(c->device));
+  const int k = c->dm.k;
+  if (s0 && s0->sync_to_device()) return MOIP_ERR_CUDA;
+  if (s1 && s1->sync_to_device()) return MOIP_ERR_CUDA;
+  if (c->q_ip.ensure((size_t)Q * k) || c->q_out.ensure(Q) || c->q_which.ensure(Q) || c->h_q.ensure((size_t)2 * Q)) return MOIP_ERR_CUDA;
+  MOIP_CUDA(cudaMemcpyAsync(c->q_ip.p, ip, sizeof(double) * Q * k, cudaMemcpyHostToDevice, c->stream));
+  DevCache e{}; e.k = k; e.size = 0; e.rec = nullptr;
+  int rc = launch_k3(s0 ? s0->view() : e, s1 ? s1->view() : e, Q, c->q_ip.p, sense, c->q_out.p, c->q_which.p, c->stream);
+  if (rc) return rc;
+  c->stats.kernel_launches += 1;
+  c->stats.cache_queries += Q;
+  MOIP_CUDA(cudaMemcpyAsync(c->h_q.p, c->q_out.p, sizeof(int) * Q, cudaMemcpyDeviceToHost, c->stream));
+  MOIP_CUDA(cudaMemcpyAsync(c->h_q.p + Q, c->q_which.p, sizeof(int) * Q, cudaMemcpyDeviceToHost, c->stream));
+  MOIP_CUDA(cudaStreamSynchronize(c->stream));
+  std::memcpy(first_match, c->h_q.p, sizeof(int) * Q);
+  if (which) std::memcpy(which, c->h_q.p + Q, sizeof(int) * Q);
+  return MOIP_OK;
+}
+
+extern "C" int moip_cache_find_batch(moip_cache* s, int Q, const double* ip, int sense, int* first_match) {
+  if (!s || Q < 0 || (Q > 0 && (!ip || !first_match))) return MOIP_ERR_ARG;
+  if (Q == 0) return MOIP_OK;
+  return cache_find2(s->ctx, s, nullptr, Q, ip, sense, first_match, nullptr);
+}
+extern "C" int moip_cache_get(const moip_cache* s, int i, double* ip, int* result, int* infeasible) {
+  if (!s || i < 0 || i >= (int)s->host.size()) return MOIP_ERR_ARG;
+  const CacheRecord& r = s->host[i];
+  for (int j = 0; j < s->k; ++j) { if (ip) ip[j] = r.ip[j]; if (result) result[j] = r.result[j]; }
+  if (infeasible) *infeasible = r.infeasible;
+  return MOIP_OK;
+}
+extern "C" int moip_cache_merge(moip_cache* s, moip_cache* other) {
+  if (!s || !other || s == other || s->k != other->k) return MOIP_ERR_ARG;
+  std::vector<CacheRecord> merged;
+  merged.reserve(s->host.size() + other->host.size());
+  merged.insert(merged.end(), other->host.begin(), other->host.end());   // splice at begin()
+  merged.insert(merged.end(), s->host.begin(), s->host.end());
+  s->host.swap(merged);
+  s->synced = 0;
+  other->host.clear();
+  other->synced = 0;
+  return MOIP_OK;
+}
+extern "C" int moip_cache_sort_unique(moip_cache* s, int* rows, int cap) {
+  if (!s) return -1;
+  const int k = s->k;
+  // Result::operator< : infeasible first, then descending lexicographic (reference src/result.cpp:9-29)
+  std::stable_sort(s->host.begin(), s->host.end(), [k](const CacheRecord& a, const CacheRecord& b) {
+    if (a.infeasible != b.infeasible) return a.infeasible > b.infeasible;
+    if (a.infeasible) return false;
+    for (int i = 0; i < k; ++i) if (a.result[i] != b.result[i]) return a.result[i] > b.result[i];
+    return false;
+  });
+  auto same = [k](const CacheRecord& a, const CacheRecord& b) {
+    if (a.infeasible != b.infeasible) return false;
+    if (a.infeasible) return true;
+    for (int i = 0; i < k; ++i) if (a.result[i] != b.result[i]) return false;
+    return true;
+  };
+  s->host.erase(std::unique(s->host.begin(), s->host.end(), same), s->host.end());
+  s->synced = 0;
+  int nrows = 0;
+  for (auto& r : s->host) {
+    if (r.infeasible) continue;
+    if (rows && nrows < cap) for (int i = 0; i < k; ++i) rows[(size_t)nrows * k + i] = r.result[i];
+    ++nrows;
+  }
+  return nrows;
+}
+
+// ------------------------------------------------------------------------------------ K4
+extern "C" int moip_verify_int64(moip_ctx* c, int B, const int32_t* x, const double* rhs, int64_t* obj_out,
+                                 uint8_t* feasible_out) {
+  if (!c || B < 0 || (B > 0 && (!x || !obj_out || !feasible_out))) return MOIP_ERR_ARG;
+  if (B == 0) return MOIP_OK;
+  MOIP_CUDA(cudaSetDevice(c->device));
+  const DevModel& d = c->dm;
+  if (c->v_x.ensure((size_t)B * d.n) || c->v_obj.ensure((size_t)B * d.k) || c->v_feas.ensure(B) ||
+      c->v_rhs.ensure((size_t)B * d.k)) return MOIP_ERR_CUDA;
+  MOIP_CUDA(cudaMemcpyAsync(c->v_x.p, x, sizeof(int) * (size_t)B * d.n, cudaMemcpyHostToDevice, c->stream));
+  if (rhs) MOIP_CUDA(cudaMemcpyAsync(c->v_rhs.p, rhs, sizeof(double) * (size_t)B * d.k, cudaMemcpyHostToDevice, c->stream));
+  int rc = launch_k4(d, B, c->v_x.p, rhs ? c->v_rhs.p : nullptr, c->v_obj.p, c->v_feas.p, c->stream);
+  if (rc) return rc;
+  c->stats.kernel_launches += 1;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+  MOIP_CUDA(cudaMemcpyAsync(obj_out, c->v_obj.p, sizeof(int64_t) * (size_t)B * d.k, cudaMemcpyDeviceToHost, c->stream));
+  MOIP_CUDA(cudaMemcpyAsync(feasible_out, c->v_feas.p, (size_t)B, cudaMemcpyDeviceToHost, c->stream));
+  MOIP_CUDA(cudaStreamSynchronize(c->stream));
+  return MOIP_OK;
+}
+
+// ------------------------------------------------------------------------------------ B&B
+int moip_ctx::ensure_pool(int slots) {
+  if (slots <= pool_slots) return MOIP_OK;
+  int ns = pool_slots ? pool_slots : 256;
+  while (ns < slots) ns *= 2;
+  if (p_lb.ensure((size_t)ns * dm.n, true, stream) || p_ub.ensure((size_t)ns * dm.n, true, stream) ||
+      p_wx.ensure((size_t)ns * dm.n, true, stream) || p_wy.ensure((size_t)ns * dm.m, true, stream)) return MOIP_ERR_CUDA;
+  for (int s = ns - 1; s >= pool_slots; --s) free_slots.push_back(s);
+  pool_slots = ns;
+  return MOIP_OK;
+}
+
+int moip_ctx::alloc_slot() {
+  if (free_slots.empty()) {
+    if (ensure_pool(pool_slots ? pool_slots * 2 : 256)) return -1;
+  }
+  int s = free_slots.back();
+  free_slots.pop_back();
+  return s;
+}
+
+namespace {
+struct OpenNode {
+  int slot;
+  double bound;   // min-form valid lower bound inherited from the parent
+  int depth;
+};
+}  // namespace
+
+// One single-objective IP:  optimise objective `cost` s.t. the structural rows and C x (<=|>=) srhs.
+// Exactness: pruning uses only valid Lagrangian bounds from K1 and int64 propagation from K2;
+// incumbents are accepted only after exact int64 evaluation (K2 leaves / K4 rounded LP points).
+int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc_x_in, IpResult& out) {
+  MOIP_CUDA(cudaSetDevice(device));
+  const Model& M = model->M;
+  const int n = dm.n, k = dm.k, m = dm.m;
+  const double sgn = dm.sgn;
+  stats.ip_solved += 1;
+  out.status = MOIP_MIP_INFEASIBLE;
+  out.x.clear();
+  if (M.int_infeasible) return MOIP_OK;
+  // integer limits of the k objective rows (model space)
+  std::vector<long long> olo(k, LLONG_MIN), ohi(k, LLONG_MAX);
+  for (int o = 0; o < k; ++o) {
+    if (std::fabs(srhs[o]) >= 1e19) continue;
+    if (M.sense == 0) ohi[o] = (long long)std::floor(srhs[o] + 1e-9);
+    else olo[o] = (long long)std::ceil(srhs[o] - 1e-9);
+  }
+  // incumbent (min-form value)
+  bool have_inc = false;
+  long long inc_val = LLONG_MAX;
+  std::vector<int> inc_x;
+  if (inc_x_in && (int)inc_x_in->size() == n) {
+    long long v = 0;
+    for (int j = 0; j < n; ++j) v += M.ci[(size_t)cost * n + j] * (long long)(*inc_x_in)[j];
+    have_inc = true; inc_val = (long long)sgn * v; inc_x = *inc_x_in;
+  }
+  // batch geometry
+  int Bmax = bb_batch > 0 ? bb_batch : num_sms * 4;
+  if (ensure_pool(std::max(256, 4 * Bmax))) return MOIP_ERR_CUDA;
+  int rc = 0;
+  rc |= r_ids.ensure((size_t)Bmax + 1); rc |= r_flag.ensure(Bmax); rc |= r_lb.ensure((size_t)Bmax * n); rc |= r_ub.ensure((size_t)Bmax * n);
+  rc |= r_status.ensure(Bmax); rc |= r_iters.ensure(Bmax); rc |= r_branch.ensure(Bmax); rc |= r_xr.ensure((size_t)Bmax * n);
+  rc |= r_counter.ensure(1); rc |= r_wx.ensure((size_t)Bmax * n); rc |= r_wy.ensure((size_t)Bmax * m);
+  rc |= r_x.ensure((size_t)Bmax * n); rc |= r_y.ensure((size_t)Bmax * m); rc |= r_pobj.ensure(Bmax); rc |= r_dbound.ensure(Bmax);
+  rc |= r_bval.ensure(Bmax); rc |= r_rhs.ensure(k); rc |= r_cutoff.ensure(1); rc |= r_leaf.ensure((size_t)Bmax * k);
+  rc |= r_olo.ensure(k); rc |= r_ohi.ensure(k); rc |= r_cobj.ensure((size_t)Bmax * k); rc |= r_cfeas.ensure(Bmax);
+  rc |= r_ops.ensure((size_t)2 * Bmax);
+  // packed D2H layout per round
+  const size_t off_flag = 0, off_status = off_flag + sizeof(int) * Bmax, off_iters = off_status + sizeof(int) * Bmax,
+               off_branch = off_iters + sizeof(int) * Bmax, off_dbound = off_branch + sizeof(int) * Bmax,
+               off_bval = off_dbound + sizeof(double) * Bmax, off_leaf = off_bval + sizeof(double) * Bmax,
+               off_cobj = off_leaf + sizeof(long long) * Bmax * k, off_cfeas = off_cobj + sizeof(long long) * Bmax * k,
+               off_end = off_cfeas + Bmax;
+  rc |= h_round.ensure(off_end + 64);
+  if (rc) return MOIP_ERR_CUDA;
+  PoolView pool{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
+
+  MOIP_CUDA(cudaMemcpyAsync(r_rhs.p, srhs, sizeof(double) * k, cudaMemcpyHostToDevice, stream));
+  MOIP_CUDA(cudaMemcpyAsync(r_ids.p + Bmax, &cost, sizeof(int), cudaMemcpyHostToDevice, stream));
+  MOIP_CUDA(cudaStreamSynchronize(stream));   // srhs / cost are caller stack memory
+  // root node
+  std::vector<OpenNode> open;
+  {
+    int s = alloc_slot();
+    if (s < 0) return MOIP_ERR_CUDA;
+    pool = PoolView{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
+    MOIP_CUDA(cudaMemcpyAsync(pool.lb + (size_t)s * n, dm.lbI, sizeof(int) * n, cudaMemcpyDeviceToDevice, stream));
+    MOIP_CUDA(cudaMemcpyAsync(pool.ub + (size_t)s * n, dm.ubI, sizeof(int) * n, cudaMemcpyDeviceToDevice, stream));
+    if ((int)root_x[cost].size() == n) {
+      MOIP_CUDA(cudaMemcpyAsync(pool.wx + (size_t)s * n, root_x[cost].data(), sizeof(double) * n, cudaMemcpyHostToDevice, stream));
+      MOIP_CUDA(cudaMemcpyAsync(pool.wy + (size_t)s * m, root_y[cost].data(), sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    } else {
+      MOIP_CUDA(cudaMemsetAsync(pool.wx + (size_t)s * n, 0, sizeof(double) * n, stream));
+      MOIP_CUDA(cudaMemsetAsync(pool.wy + (size_t)s * m, 0, sizeof(double) * m, stream));
+    }
+    open.push_back({s, -HUGE_VAL, 0});
+  }
+  std::vector<int> ids;
+  std::vector<OpenNode> batch;
+  std::vector<BranchOp> ops;
+  std::vector<int> to_free;
+  bool first_round = true;
+  LpParams lp{};
+  lp.eps = bb_eps; lp.max_iter = bb_max_iter; lp.check_every = bb_check; lp.fixed_iters = 0;
+  lp.norm_every = norm_every > 0 ? norm_every : 1; lp.cutoff_slack = 1.0 - 1e-6;
+
+  auto prunable = [&](double bound) {
+    return have_inc && bound > -HUGE_VAL && std::ceil(bound - 1e-6) >= (double)inc_val;
+  };
+
+  while (!open.empty()) {
+    // ---- select the batch: dive (deepest first) until an incumbent exists, then best bound first
+    if (have_inc)
+      std::sort(open.begin(), open.end(), [](const OpenNode& a, const OpenNode& b) {
+        if (a.bound != b.bound) return a.bound > b.bound;      // best (smallest) bound at the back
+        return a.depth < b.depth;
+      });
+    else
+      std::sort(open.begin(), open.end(), [](const OpenNode& a, const OpenNode& b) {
+        if (a.depth != b.depth) return a.depth < b.depth;      // deepest at the back
+        return a.bound > b.bound;
+      });
+    batch.clear(); ids.clear();
+    while (!open.empty() && (int)batch.size() < Bmax) {
+      OpenNode nd = open.back();
+      open.pop_back();
+      if (prunable(nd.bound)) { free_slots.push_back(nd.slot); continue; }
+      batch.push_back(nd);
+      ids.push_back(nd.slot);
+    }
+    const int B = (int)batch.size();
+    if (B == 0) break;
+    stats.bb_nodes += B;
+    // ---- device round: propagate -> gather -> LP -> scatter/round -> verify
+    std::vector<long long> plo = olo, phi = ohi;
+    if (have_inc) {   // incumbent cut-off row on the optimised objective: must be strictly better
+      if (M.sense == 0) phi[cost] = std::min(phi[cost], inc_val - 1);
+      else plo[cost] = std::max(plo[cost], -inc_val + 1);
+    }
+    MOIP_CUDA(cudaMemcpyAsync(r_ids.p, ids.data(), sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+    MOIP_CUDA(cudaMemcpyAsync(r_olo.p, plo.data(), sizeof(long long) * k, cudaMemcpyHostToDevice, stream));
+    MOIP_CUDA(cudaMemcpyAsync(r_ohi.p, phi.data(), sizeof(long long) * k, cudaMemcpyHostToDevice, stream));
+    double cut = have_inc ? (double)inc_val : HUGE_VAL;
+    MOIP_CUDA(cudaMemcpyAsync(r_cutoff.p, &cut, sizeof(double), cudaMemcpyHostToDevice, stream));
+    // (the H2D sources above are host vectors/locals that stay alive until the sync below)
+    if (launch_k2_propagate(dm, pool, B, r_ids.p, r_olo.p, r_ohi.p, 16, r_flag.p, r_leaf.p, stream)) return MOIP_ERR_CUDA;
+    if (launch_k2_gather(dm, pool, B, r_ids.p, r_lb.p, r_ub.p, r_wx.p, r_wy.p, stream)) return MOIP_ERR_CUDA;
+    LpBatch b{};
+    b.B = B; b.cost_idx = nullptr; b.rhs = r_rhs.p; b.lb = r_lb.p; b.ub = r_ub.p;
+    b.warm_x = r_wx.p; b.warm_y = r_wy.p; b.out_x = r_x.p; b.out_y = r_y.p;
+    b.primal_obj = r_pobj.p; b.dual_bound = r_dbound.p; b.status = r_status.p; b.iters = r_iters.p;
+    b.branch_var = r_branch.p; b.branch_val = r_bval.p; b.skip = r_flag.p;
+    b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = r_cutoff.p; b.work_counter = r_counter.p;
+    b.cost_idx = r_ids.p + Bmax;   // one shared cost index, staged behind the ids (cost_stride = 0)
+    if (launch_k1(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
+    if (launch_k2_scatter_round(dm, pool, B, r_ids.p, r_x.p, r_y.p, r_xr.p, stream)) return MOIP_ERR_CUDA;
+    if (launch_k4(dm, B, r_xr.p, nullptr, r_cobj.p, r_cfeas.p, stream)) return MOIP_ERR_CUDA;
+    stats.kernel_launches += 5;
+    unsigned char* H = h_round.p;
+    MOIP_CUDA(cudaMemcpyAsync(H + off_flag, r_flag.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_status, r_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_iters, r_iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_branch, r_branch.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_dbound, r_dbound.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_bval, r_bval.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_leaf, r_leaf.p, sizeof(long long) * B * k, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_cobj, r_cobj.p, sizeof(long long) * B * k, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_cfeas, r_cfeas.p, (size_t)B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaStreamSynchronize(stream));
+    const int* flag = (const int*)(H + off_flag);
+    const int* status = (const int*)(H + off_status);
+    const int* iters = (const int*)(H + off_iters);
+    const int* branch = (const int*)(H + off_branch);
+    const double* dbound = (const double*)(H + off_dbound);
+    const double* bval = (const double*)(H + off_bval);
+    const long long* leaf = (const long long*)(H + off_leaf);
+    const long long* cobj = (const long long*)(H + off_cobj);
+    const unsigned char* cfeas = H + off_cfeas;
+    // ---- incumbent candidates of this round (exactly evaluated on the device)
+    int best_src = -1; bool best_is_leaf = false;
+    long long best_val = inc_val;
+    auto within = [&](const long long* ov) {
+      for (int o = 0; o < k; ++o) if (ov[o] < olo[o] || ov[o] > ohi[o]) return false;
+      return true;
+    };
+    for (int i = 0; i < B; ++i) {
+      if (flag[i] == 2) {
+        const long long v = (long long)sgn * leaf[(size_t)i * k + cost];
+        if (v < best_val) { best_val = v; best_src = i; best_is_leaf = true; }
+      } else if (flag[i] == 0) {
+        stats.node_lps += 1;
+        stats.lp_iterations += iters[i];
+        if (cfeas[i] && within(cobj + (size_t)i * k)) {
+          const long long v = (long long)sgn * cobj[(size_t)i * k + cost];
+          if (v < best_val) { best_val = v; best_src = i; best_is_leaf = false; }
+        }
+      }
+    }
+    if (best_src >= 0) {
+      inc_x.resize(n);
+      const int* src = best_is_leaf ? pool.lb + (size_t)ids[best_src] * n : r_xr.p + (size_t)best_src * n;
+      MOIP_CUDA(cudaMemcpyAsync(inc_x.data(), src, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaStreamSynchronize(stream));
+      inc_val = best_val; have_inc = true;
+    }
+    if (first_round && flag[0] == 0) {   // remember the root iterate as warm start for the next IP on this objective
+      root_x[cost].resize(n); root_y[cost].resize(m);
+      MOIP_CUDA(cudaMemcpyAsync(root_x[cost].data(), r_x.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaMemcpyAsync(root_y[cost].data(), r_y.p, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaStreamSynchronize(stream));
+    }
+    first_round = false;
+    // ---- branch
+    ops.clear(); to_free.clear();
+    for (int i = 0; i < B; ++i) {
+      const OpenNode& nd = batch[i];
+      to_free.push_back(nd.slot);
+      if (flag[i] != 0) continue;                                  // infeasible or leaf: done
+      if (status[i] == MOIP_LP_CUTOFF || status[i] == MOIP_LP_INFEASIBLE) continue;
+      const double lbnd = std::max(nd.bound, dbound[i]);
+      if (prunable(lbnd)) continue;
+      int var = branch[i];
+      double val = bval[i];
+      if (var < 0) {
+        // LP point is integral.  If its rounding is feasible and attains ceil(bound) the node is solved.
+        if (cfeas[i] && within(cobj + (size_t)i * k) &&
+            (double)((long long)sgn * cobj[(size_t)i * k + cost]) <= std::ceil(lbnd - 1e-6)) continue;
+        var = -2;   // pick the first unfixed column on the host side (needs the node's bounds)
+      }
+      if (var == -2) {
+        // rare path: fetch the node's bounds and branch on the first unfixed column at its midpoint
+        std::vector<int> nlb(n), nub(n);
+        MOIP_CUDA(cudaMemcpyAsync(nlb.data(), pool.lb + (size_t)nd.slot * n, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+        MOIP_CUDA(cudaMemcpyAsync(nub.data(), pool.ub + (size_t)nd.slot * n, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+        MOIP_CUDA(cudaStreamSynchronize(stream));
+        var = -1;
+        for (int j = 0; j < n; ++j) if (nlb[j] < nub[j]) { var = j; val = 0.5 * ((double)nlb[j] + (double)nub[j]); break; }
+        if (var < 0) continue;   // fully fixed: K2 will have classified it as a leaf
+      }
+      const int fl = (int)std::floor(val);
+      const int c0 = alloc_slot(), c1 = alloc_slot();
+      if (c0 < 0 || c1 < 0) return MOIP_ERR_CUDA;
+      pool = PoolView{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
+      ops.push_back({nd.slot, c0, var, INT_MIN, fl});
+      ops.push_back({nd.slot, c1, var, fl + 1, INT_MAX});
+      // the child closer to the LP value is explored first when diving (pushed last)
+      const bool up_first = (val - fl) >= 0.5;
+      OpenNode a{c0, lbnd, nd.depth + 1}, bnode{c1, lbnd, nd.depth + 1};
+      if (up_first) { open.push_back(a); open.push_back(bnode); } else { open.push_back(bnode); open.push_back(a); }
+    }
+    if (!ops.empty()) {
+      MOIP_CUDA(cudaMemcpyAsync(r_ops.p, ops.data(), sizeof(BranchOp) * ops.size(), cudaMemcpyHostToDevice, stream));
+      if (launch_k2_branch(dm, pool, (int)ops.size(), r_ops.p, stream)) return MOIP_ERR_CUDA;
+      stats.kernel_launches += 1;
+      MOIP_CUDA(cudaStreamSynchronize(stream));   // ops (host vector) is reused next round
+    }
+    for (int s : to_free) free_slots.push_back(s);
+  }
+  for (auto& nd : open) free_slots.push_back(nd.slot);
+  if (have_inc) {
+    out.status = MOIP_MIP_OPTIMAL;
+    out.obj = (long long)sgn * inc_val;
+    out.x = inc_x;
+  }
+  return MOIP_OK;
+}
+
+// int solve(Env&, Problem&, int* result, double* rhs, Thread* t)  -- reference src/aira.cpp:452-536
+int moip_ctx::lex_solve(const int* perm, int n_obj, const double* rhs, int* result, int* mip_status) {
+  const Model& M = model->M;
+  const int k = dm.k, n = dm.n;
+  const double t0 = now_s();
+  std::vector<double> srhs(rhs, rhs + k);            // :457-462
+  std::vector<int> x;
+  int st = MOIP_MIP_INFEASIBLE;
+  for (int jp = 0; jp < n_obj; ++jp) {               // :467
+    const int j = perm[jp];
+    IpResult r;
+    int rc = solve_ip(j, srhs.data(), x.empty() ? nullptr : &x, r);
+    if (rc) return rc;
+    st = r.status;
+    if (st == MOIP_MIP_INFEASIBLE) break;            // :489-492
+    x = r.x;
+    result[j] = (int)r.obj;                          // :517 (exact, no rounding needed)
+    srhs[j] = (double)r.obj;
+  }
+  if (st != MOIP_MIP_INFEASIBLE) {
+    for (int jp = n_obj; jp < k; ++jp) {             // :520-530
+      const int j = perm[jp];
+      long long v = 0;
+      for (int q = 0; q < n; ++q) v += M.ci[(size_t)j * n + q] * (long long)x[q];
+      result[j] = (int)v;
+    }
+  }
+  if (mip_status) *mip_status = st;
+  stats.solver_seconds += now_s() - t0;
+  return MOIP_OK;
+}
+
+// void get_limit(Env&, Problem&, int obj, double* rhs, int* result, Sense) -- reference src/aira.cpp:367-450
+int moip_ctx::get_limit(int obj, int sense, const double* rhs, int* result, int* mip_status) {
+  const Model& M = model->M;
+  if (sense != M.sense) {
+    std::fprintf(stderr, "moip_b200: get_limit with a sense different from the model's is not supported\n");
+    return MOIP_ERR_UNSUPPORTED;
+  }
+  const double t0 = now_s();
+  IpResult r;
+  int rc = solve_ip(obj, rhs, nullptr, r);
+  if (rc) return rc;
+  if (mip_status) *mip_status = r.status;
+  if (r.status != MOIP_MIP_INFEASIBLE) {             // :437-447; untouched when infeasible (:410-412)
+    for (int j = 0; j < dm.k; ++j) {
+      long long v = 0;
+      for (int q = 0; q < dm.n; ++q) v += M.ci[(size_t)j * dm.n + q] * (long long)r.x[q];
+      result[j] = (int)v;
+    }
+  }
+  stats.solver_seconds += now_s() - t0;
+  return MOIP_OK;
+}
+
+extern "C" int moip_lex_solve(moip_ctx* c, const int* perm, int n_obj, const double* rhs, int* result, int* mip_status) {
+  if (!c || !perm || !rhs || !result || n_obj < 1 || n_obj > c->dm.k) return MOIP_ERR_ARG;
+  for (int i = 0; i < c->dm.k; ++i) if (perm[i] < 0 || perm[i] >= c->dm.k) return MOIP_ERR_ARG;
+  return c->lex_solve(perm, n_obj, rhs, result, mip_status);
+}
+extern "C" int moip_get_limit(moip_ctx* c, int obj, int sense, const double* rhs, int* result, int* mip_status) {
+  if (!c || !rhs || !result || obj < 0 || obj >= c->dm.k) return MOIP_ERR_ARG;
+  return c->get_limit(obj, sense, rhs, result, mip_status);
+}

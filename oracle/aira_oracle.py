@@ -292,13 +292,15 @@ def optimise(model: Model, oracle, all_sols: Solutions, infeasibles: Solutions, 
         (all_sols if split else s).insert(rhs, result, False)      # :647-650
     if trace is not None:
         trace.append((tuple(rhs), False, status == CPXMIP_INFEASIBLE, None if result is None else tuple(result)))
+    if status == CPXMIP_INFEASIBLE:
+        # nothing lies inside these bounds; the reference's max[]/min[] trackers are uninitialised
+        # from here on (:693-697), so the defined behaviour is to stop
+        all_sols.merge(s)
+        return
     if split:
         t.split_stop += -1 if MIN else 1                           # :653-657
-    mx = [0] * k
-    mn = [0] * k
-    if status != CPXMIP_INFEASIBLE:
-        mx = list(result)
-        mn = list(result)                                          # :693-697
+    mx = list(result)
+    mn = list(result)                                              # :693-697
 
     def step(d):
         """rhs[d] = max[d]-1 ; max[d] = INT_MIN (MIN) / mirrored (MAX), with int32 wrap."""
