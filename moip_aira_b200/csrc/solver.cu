@@ -249,13 +249,13 @@ DevCache moip_cache::view() const {
 extern "C" int moip_cache_create(moip_ctx* c, moip_cache** out) {
   if (!c || !out) return MOIP_ERR_ARG;
   moip_cache* s = new moip_cache();
-  s->ctx = c; s->k = c->dm.k;
+  s->ctx = c; s->k = c->dm.k; s->device = c->device;
   *out = s;
   return MOIP_OK;
 }
 extern "C" void moip_cache_destroy(moip_cache* s) {
   if (!s) return;
-  cudaSetDevice(s->ctx->device);
+  cudaSetDevice(s->device);
   s->dev.release();
   delete s;
 }

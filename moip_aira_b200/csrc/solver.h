@@ -62,6 +62,7 @@ struct IpResult {
 
 struct moip_cache {
   moip_ctx* ctx = nullptr;
+  int device = 0;                        // copy: the cache may outlive its context
   int k = 0;
   std::vector<moip::CacheRecord> host;   // insertion order
   moip::DBuf<moip::CacheRecord> dev;

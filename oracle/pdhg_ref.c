@@ -24,6 +24,8 @@ typedef struct {
   double *S;      /* scaled matrix m x n */
   double *dr, *dc;
   double eta;
+  int *ptr, *col;   /* CSR of the nonzeros of S (the CPU port exploits sparsity like the kernel) */
+  double *val;
 } scaled_t;
 
 static double clampd(double v, double a, double b) { return fmin(fmax(v, a), b); }
@@ -74,6 +76,18 @@ static void scale_model(int m, int n, const double* K, scaled_t* s) {
   if (sig <= 0) sig = 1.0;
   s->eta = 0.98 / sig;
   free(r); free(c); free(v); free(u); free(w);
+  int nnz = 0;
+  for (size_t q = 0; q < (size_t)m * n; ++q) nnz += s->S[q] != 0.0;
+  s->ptr = (int*)malloc(sizeof(int) * (m + 1));
+  s->col = (int*)malloc(sizeof(int) * (nnz > 0 ? nnz : 1));
+  s->val = (double*)malloc(sizeof(double) * (nnz > 0 ? nnz : 1));
+  nnz = 0;
+  for (int i = 0; i < m; ++i) {
+    s->ptr[i] = nnz;
+    for (int j = 0; j < n; ++j)
+      if (s->S[(size_t)i * n + j] != 0.0) { s->col[nnz] = j; s->val[nnz] = s->S[(size_t)i * n + j]; ++nnz; }
+  }
+  s->ptr[m] = nnz;
 }
 
 /* one node LP on a pre-scaled model; lo/hi/l/u/c are UNSCALED, per node */
@@ -83,9 +97,9 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
                        double* x_out, double* y_out, double* pobj_out, double* lb_out, int* iters_out, int* status_out) {
   const int n = s->n, m = s->m;
   const double eta = s->eta;
-  double* buf = (double*)calloc((size_t)(6 * n + 8 * m), sizeof(double));
+  double* buf = (double*)calloc((size_t)(7 * n + 8 * m), sizeof(double));
   double *x = buf, *xa = x + n, *xbar = xa + n, *l = xbar + n, *u = l + n, *c = u + n;
-  double *y = c + n, *ya = y + m, *yt = ya + m, *sx = yt + m, *sxa = sx + m, *sxt = sxa + m, *lo = sxt + m, *hi = lo + m;
+  double *y = c + n, *ya = y + m, *yt = ya + m, *sx = yt + m, *sxa = sx + m, *sxt = sxa + m, *lo = sxt + m, *hi = lo + m, *g = hi + m;
   double c2 = 0, obj_upper = 0, bn2 = 0, bn2_un = 0;
   for (int j = 0; j < n; ++j) {
     l[j] = l_un[j] / s->dc[j]; u[j] = u_un[j] / s->dc[j];
@@ -102,7 +116,7 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
     double tu = !isinf(hi_un[i]) ? hi_un[i] : (!isinf(lo_un[i]) ? lo_un[i] : 0.0);
     bn2_un += tu * tu;
     double q = 0;
-    for (int j = 0; j < n; ++j) q += s->S[(size_t)i * n + j] * x[j];
+    for (int e = s->ptr[i]; e < s->ptr[i + 1]; ++e) q += s->val[e] * x[s->col[e]];
     sx[i] = q; sxa[i] = q;
   }
   double w = (c2 > 0 && bn2 > 0) ? sqrt(c2 / bn2) : 1.0;
@@ -115,17 +129,21 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
     ++it;
     const int norm_it = (kk == 0) || (kk % norm_every == 0);
     double dx2 = 0;
+    for (int j = 0; j < n; ++j) g[j] = 0;
+    for (int i = 0; i < m; ++i) {
+      const double yi = y[i];
+      if (yi != 0.0) for (int e = s->ptr[i]; e < s->ptr[i + 1]; ++e) g[s->col[e]] += s->val[e] * yi;
+    }
     for (int j = 0; j < n; ++j) {
-      double g = 0;
-      for (int i = 0; i < m; ++i) g += s->S[(size_t)i * n + j] * y[i];
-      double xt = clampd(x[j] - tau * (c[j] - g), l[j], u[j]);
+      double xt = clampd(x[j] - tau * (c[j] - g[j]), l[j], u[j]);
       xbar[j] = 2.0 * xt - x[j];
       dx2 += (xt - x[j]) * (xt - x[j]);
     }
     double dy2 = 0, cross = 0;
     for (int i = 0; i < m; ++i) {
       double q = 0;
-      for (int j = 0; j < n; ++j) q += s->S[(size_t)i * n + j] * xbar[j];
+      if (!(isinf(lo[i]) && isinf(hi[i])))
+        for (int e = s->ptr[i]; e < s->ptr[i + 1]; ++e) q += s->val[e] * xbar[s->col[e]];
       double sxti = 0.5 * (q + sx[i]);
       double v = y[i] / sigma - q;
       double yti = sigma * (v - clampd(v, -hi[i], -lo[i]));
@@ -143,10 +161,13 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
     int stop = 0;
     if ((fixed_iters <= 0 && (it % check_every) == 0) || (fixed_iters > 0 && it >= iter_cap)) {
       double po = 0, dcol = 0, drow = 0, pres2 = 0;
+      for (int j = 0; j < n; ++j) g[j] = 0;
+      for (int i = 0; i < m; ++i) {
+        const double yi = yt[i];
+        if (yi != 0.0) for (int e = s->ptr[i]; e < s->ptr[i + 1]; ++e) g[s->col[e]] += s->val[e] * yi;
+      }
       for (int j = 0; j < n; ++j) {
-        double g = 0;
-        for (int i = 0; i < m; ++i) g += s->S[(size_t)i * n + j] * yt[i];
-        double r = c[j] - g;
+        double r = c[j] - g[j];
         po += c[j] * 0.5 * (xbar[j] + x[j]);
         dcol += (r > 0) ? r * l[j] : r * u[j];
       }
@@ -233,6 +254,6 @@ int pdhg_ref_batch(int m, int n, const double* K, int B, const double* c, const 
   worker_main(&j);
   for (int t = 1; t < nt; ++t) pthread_join(th[t], NULL);
   free(th);
-  free(s.S); free(s.dr); free(s.dc);
+  free(s.S); free(s.dr); free(s.dc); free(s.ptr); free(s.col); free(s.val);
   return nt;
 }
