@@ -35,6 +35,19 @@ struct DevModel {
   const double* s_hi;
   const double* dr;           // [m]
   const double* dc;           // [n]
+  // fast-kernel image (rows in kernel order: short structural | k objective | long structural)
+  int fast_ok, msS, nL, KD, RW, ell2_w;
+  const double* rowell_val;   // [RW][msS]
+  const int* rowell_col;
+  const double* ellT2_val;    // [ell2_w][n]
+  const int* ellT2_row;
+  const double* D2;           // [KD][n]
+  int col_units;
+  const double* colrec;       // [n][col_units] packed column records (see model.h)
+  const double* rowrec;       // [RW][msS][2]   packed row-ELL entries
+  const double* dr_k;         // [m]
+  const double* lo_k;         // [m] scaled structural bounds in kernel order
+  const double* hi_k;
   // exact integer image
   const long long* ai_val;    // [nnz] (pattern s_ptr/s_col)
   const long long* ri_lo;     // [ms]  LLONG_MIN = free
@@ -76,6 +89,7 @@ struct LpParams {
   double cutoff_slack;        // stop when bound >= cutoff - slack (integer objectives: 1 - 1e-6)
 };
 
+int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_expand_masks(const DevModel& dm, int B, const uint32_t* masks, int mask_words, int* lb, int* ub,
                         cudaStream_t st);

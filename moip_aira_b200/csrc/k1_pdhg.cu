@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
       bool restart = false;
       if (norm_it) {
         block_sum<2, NT>(aB, redB, tid);            // barrier: yt, sxt visible
-        const double fp = sqrt(fmax(0.0, (w / eta) * aA[0] - 2.0 * aB[1] + aB[0] / (eta * w)));
+        const double fp = fmax(0.0, (w / eta) * aA[0] - 2.0 * aB[1] + aB[0] / (eta * w));   // squared
         if (kk == 0) r0 = fp;
-        else if (fp <= 0.2 * r0 || (fp <= 0.8 * r0 && rprev >= 0.0 && fp > rprev) || (double)kk >= 0.36 * (double)it)
+        else if (fp <= 0.04 * r0 || (fp <= 0.64 * r0 && rprev >= 0.0 && fp > rprev) || 25 * kk >= 9 * it)
           restart = true;
         rprev = fp;
       } else {

@@ -493,6 +493,76 @@ int finalize_model(Model& M, std::string& err) {
     double b = M.rhs[i] * M.dr[i];
     M.norm_row_bounds2 += b * b;
   }
+  // ---- fast-kernel image ----------------------------------------------------------------------
+  {
+    const int long_thr = std::max(32, n / 8);
+    std::vector<int> shortr, longr;
+    for (int i = 0; i < ms; ++i) ((M.a_ptr[i + 1] - M.a_ptr[i]) > long_thr ? longr : shortr).push_back(i);
+    M.msS = (int)shortr.size(); M.nL = (int)longr.size(); M.KD = k + M.nL;
+    M.krow.clear();
+    for (int i : shortr) M.krow.push_back(i);
+    for (int o = 0; o < k; ++o) M.krow.push_back(ms + o);
+    for (int i : longr) M.krow.push_back(i);
+    M.dr_k.assign(m, 1.0); M.lo_k.assign(m, -HUGE_VAL); M.hi_k.assign(m, HUGE_VAL);
+    for (int r2 = 0; r2 < m; ++r2) {
+      const int i = M.krow[r2];
+      M.dr_k[r2] = M.dr[i];
+      if (i < ms) { M.lo_k[r2] = M.s_lo[i]; M.hi_k[r2] = M.s_hi[i]; }
+    }
+    M.RW = 0;
+    for (int i : shortr) M.RW = std::max(M.RW, M.a_ptr[i + 1] - M.a_ptr[i]);
+    M.rowell_val.assign((size_t)std::max(1, M.RW) * std::max(1, M.msS), 0.0);
+    M.rowell_col.assign((size_t)std::max(1, M.RW) * std::max(1, M.msS), 0);
+    std::vector<int> ccnt(n, 0);
+    for (int r2 = 0; r2 < M.msS; ++r2) {
+      const int i = shortr[r2];
+      int e = 0;
+      for (int q = M.a_ptr[i]; q < M.a_ptr[i + 1]; ++q, ++e) {
+        M.rowell_val[(size_t)e * M.msS + r2] = M.s_val[q];
+        M.rowell_col[(size_t)e * M.msS + r2] = M.a_col[q];
+        ++ccnt[M.a_col[q]];
+      }
+    }
+    M.ell2_w = 0;
+    for (int j = 0; j < n; ++j) M.ell2_w = std::max(M.ell2_w, ccnt[j]);
+    M.ellT2_val.assign((size_t)std::max(1, M.ell2_w) * n, 0.0);
+    M.ellT2_row.assign((size_t)std::max(1, M.ell2_w) * n, 0);
+    std::fill(ccnt.begin(), ccnt.end(), 0);
+    for (int r2 = 0; r2 < M.msS; ++r2) {
+      const int i = shortr[r2];
+      for (int q = M.a_ptr[i]; q < M.a_ptr[i + 1]; ++q) {
+        const int j = M.a_col[q], e = ccnt[j]++;
+        M.ellT2_val[(size_t)e * n + j] = M.s_val[q];
+        M.ellT2_row[(size_t)e * n + j] = r2;
+      }
+    }
+    M.D2.assign((size_t)M.KD * n, 0.0);
+    for (int o = 0; o < k; ++o) for (int j = 0; j < n; ++j) M.D2[(size_t)o * n + j] = M.D[(size_t)o * n + j];
+    for (int t = 0; t < M.nL; ++t) {
+      const int i = longr[t];
+      for (int q = M.a_ptr[i]; q < M.a_ptr[i + 1]; ++q) M.D2[(size_t)(k + t) * n + M.a_col[q]] += M.s_val[q];
+    }
+    M.fast_ok = M.KD <= 6 && M.ell2_w <= 2 && m <= 128;
+    const int E = M.ell2_w;
+    const int uc = E + M.KD + (E + 1) / 2;
+    M.col_units = (uc + 1) & ~1;
+    M.colrec.assign((size_t)n * M.col_units, 0.0);
+    for (int j = 0; j < n; ++j) {
+      double* rec = M.colrec.data() + (size_t)j * M.col_units;
+      for (int e = 0; e < E; ++e) rec[e] = M.ellT2_val[(size_t)e * n + j];
+      for (int d = 0; d < M.KD; ++d) rec[E + d] = M.D2[(size_t)d * n + j];
+      int32_t* ids = reinterpret_cast<int32_t*>(rec + E + M.KD);
+      for (int e = 0; e < E; ++e) ids[e] = M.ellT2_row[(size_t)e * n + j];
+    }
+    M.rowrec.assign((size_t)std::max(1, M.RW) * std::max(1, M.msS) * 2, 0.0);
+    for (int e = 0; e < M.RW; ++e)
+      for (int r2 = 0; r2 < M.msS; ++r2) {
+        double* rec = M.rowrec.data() + ((size_t)e * M.msS + r2) * 2;
+        rec[0] = M.rowell_val[(size_t)e * M.msS + r2];
+        int32_t* id = reinterpret_cast<int32_t*>(rec + 1);
+        id[0] = M.rowell_col[(size_t)e * M.msS + r2]; id[1] = 0;
+      }
+  }
   return 0;
 }
 

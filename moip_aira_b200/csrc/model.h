@@ -46,6 +46,21 @@ struct Model {
   // dense objective block D = Dr[ms..] * sgn*C * Dc  (k*n)
   std::vector<double> D;
   std::vector<double> s_lo, s_hi;      // scaled structural row bounds (+-inf as +-HUGE_VAL)
+  // ---- fast-kernel image: rows reordered as [short structural | k objective | long structural]
+  bool fast_ok = false;                // false -> generic kernel (too many long rows / wide rows)
+  int msS = 0, nL = 0, KD = 0, RW = 0, ell2_w = 0;
+  std::vector<int> krow;               // kernel row -> original row (ms + o for objective o)
+  std::vector<double> dr_k;            // [m] row scaling in kernel order
+  std::vector<double> lo_k, hi_k;      // [m] scaled row bounds in kernel order (objective rows: per node)
+  std::vector<double> rowell_val;      // [RW][msS] short rows of S, row-ELL
+  std::vector<int> rowell_col;
+  std::vector<double> ellT2_val;       // [ell2_w][n] short rows of S^T, column-ELL (row ids in kernel order)
+  std::vector<int> ellT2_row;
+  std::vector<double> D2;              // [KD][n] dense rows: k objectives then the long structural rows
+  // packed images the fast kernel actually reads (16-byte vector loads, one address per column/entry)
+  int col_units = 0;                   // 8-byte units per column record (even)
+  std::vector<double> colrec;          // [n][col_units]: ell2_w values | KD dense values | ell2_w row ids (int32 pairs)
+  std::vector<double> rowrec;          // [RW][msS][2]: {value, column id (int32 in the low half)}
   double eta = 0;                      // 0.99 / ||S||_2
   double norm_row_bounds2 = 0;         // sum of squares of finite scaled structural bounds
 };

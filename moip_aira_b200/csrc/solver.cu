@@ -84,6 +84,19 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   rc |= upload(c, M.s_hi, &d.s_hi);
   rc |= upload(c, M.dr, &d.dr);
   rc |= upload(c, M.dc, &d.dc);
+  d.fast_ok = M.fast_ok ? 1 : 0; d.msS = M.msS; d.nL = M.nL; d.KD = M.KD; d.RW = M.RW; d.ell2_w = M.ell2_w;
+  if (std::getenv("MOIP_K1_GENERIC")) d.fast_ok = 0;
+  rc |= upload(c, M.rowell_val, &d.rowell_val);
+  rc |= upload(c, M.rowell_col, &d.rowell_col);
+  rc |= upload(c, M.ellT2_val, &d.ellT2_val);
+  rc |= upload(c, M.ellT2_row, &d.ellT2_row);
+  rc |= upload(c, M.D2, &d.D2);
+  d.col_units = M.col_units;
+  rc |= upload(c, M.colrec, &d.colrec);
+  rc |= upload(c, M.rowrec, &d.rowrec);
+  rc |= upload(c, M.dr_k, &d.dr_k);
+  rc |= upload(c, M.lo_k, &d.lo_k);
+  rc |= upload(c, M.hi_k, &d.hi_k);
   rc |= upload(c, ai, &d.ai_val);
   rc |= upload(c, rlo, &d.ri_lo);
   rc |= upload(c, rhi, &d.ri_hi);
@@ -97,7 +110,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->bb_max_iter = env_int("MOIP_BB_MAX_ITER", 3000);
   c->bb_eps = env_double("MOIP_BB_EPS", 1e-5);
   c->bb_check = env_int("MOIP_BB_CHECK", 32);
-  c->norm_every = env_int("MOIP_NORM_EVERY", 1);
+  c->norm_every = env_int("MOIP_NORM_EVERY", 4);
   *out = c;
   return MOIP_OK;
 }
@@ -193,7 +206,7 @@ extern "C" int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params) {
   p.cutoff_slack = 0.0;
   c->stats.kernel_launches += 1;
   c->stats.node_lps += b.B;
-  return launch_k1(d, b, p, c->num_sms, c->stream);
+  return d.fast_ok ? launch_k1_fast(d, b, p, c->num_sms, c->stream) : launch_k1(d, b, p, c->num_sms, c->stream);
 }
 
 extern "C" int moip_lp_batch_download(moip_ctx* c, double* primal_obj, double* dual_bound, int* status, int* iters,
@@ -517,7 +530,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     b.branch_var = r_branch.p; b.branch_val = r_bval.p; b.skip = r_flag.p;
     b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = r_cutoff.p; b.work_counter = r_counter.p;
     b.cost_idx = r_ids.p + Bmax;   // one shared cost index, staged behind the ids (cost_stride = 0)
-    if (launch_k1(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
+    if (dm.fast_ok ? launch_k1_fast(dm, b, lp, num_sms, stream) : launch_k1(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
     if (launch_k2_scatter_round(dm, pool, B, r_ids.p, r_x.p, r_y.p, r_xr.p, stream)) return MOIP_ERR_CUDA;
     if (launch_k4(dm, B, r_xr.p, nullptr, r_cobj.p, r_cfeas.p, stream)) return MOIP_ERR_CUDA;
     stats.kernel_launches += 5;

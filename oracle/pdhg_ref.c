@@ -153,9 +153,9 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
     }
     int restart = 0;
     if (norm_it) {
-      double fp = sqrt(fmax(0.0, (w / eta) * dx2 - 2.0 * cross + dy2 / (eta * w)));
+      double fp = fmax(0.0, (w / eta) * dx2 - 2.0 * cross + dy2 / (eta * w));   /* squared fixed-point error */
       if (kk == 0) r0 = fp;
-      else if (fp <= 0.2 * r0 || (fp <= 0.8 * r0 && rprev >= 0.0 && fp > rprev) || (double)kk >= 0.36 * (double)it) restart = 1;
+      else if (fp <= 0.04 * r0 || (fp <= 0.64 * r0 && rprev >= 0.0 && fp > rprev) || 25 * kk >= 9 * it) restart = 1;
       rprev = fp;
     }
     int stop = 0;

@@ -197,7 +197,7 @@ def test_k1_fixed_iterations_match_port(mb, tmp_path):
     cost, rhs, masks = po.sample_node_batch(model, 12, seed=3)
     for iters in (1, 7, 40):
         got = ctx.lp_batch_solve(cost, rhs, masks, mb.Context.lp_params(fixed_iters=iters), want_x=True)
-        port = po.pdhg_ref(model, cost, rhs, masks, fixed_iters=iters)
+        port = po.pdhg_ref(model, cost, rhs, masks, fixed_iters=iters, norm_every=int(os.environ.get("MOIP_NORM_EVERY", "4")))
         assert np.all(got["iters"] == iters)
         assert np.allclose(got["x"], port["x"], rtol=0, atol=1e-9)
         assert np.allclose(got["primal_obj"], port["primal_obj"], rtol=1e-10, atol=1e-9)
