@@ -21,6 +21,7 @@
 // all CTAs and served from L1/L2.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "device.h"
 
@@ -79,8 +80,8 @@ struct ColRec {
   }
 };
 
-template <int NT, int KD, int ELLW>
-__global__ void __launch_bounds__(NT, NT <= 128 ? 4 : 2)
+template <int NT, int KD, int ELLW, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lpr_log2) {
   constexpr int NW = NT / 32;
   extern __shared__ double smem[];
@@ -392,18 +393,32 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
   }
 }
 
-template <int NT, int KD, int ELLW>
+int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+template <int NT, int KD, int ELLW, int MINB>
 int launch_fast(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
+  auto kern = k1_fast_kernel<NT, KD, ELLW, MINB>;
   const size_t smem = sizeof(double) * ((size_t)CS * dm.n + (size_t)2 * dm.m + (size_t)24 * (NT / 32));
   static size_t configured = 0;
+  static int occ = 1;
   if (smem > configured) {
-    MOIP_CUDA(cudaFuncSetAttribute(k1_fast_kernel<NT, KD, ELLW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MOIP_CUDA(cudaFuncSetAttribute(k1_fast_kernel<NT, KD, ELLW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // leave the rest of the 256 KB array to L1: the packed model image (tens of KB) is re-read by every
+    // CTA every iteration and must hit there
+    MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MOIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) { std::fprintf(stderr, "moip_b200: node LP does not fit in shared memory (n=%d)\n", dm.n); return MOIP_ERR_LIMIT; }
+    const int cap = env_int("MOIP_K1_OCC", 0);
+    if (cap > 0 && cap < occ) occ = cap;
+    int pct = (int)(((smem + 1024) * occ * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    pct = env_int("MOIP_K1_CARVEOUT_PCT", pct);
+    MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     configured = smem;
   }
-  int occ = 1;
-  MOIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_fast_kernel<NT, KD, ELLW>, NT, smem));
-  if (occ < 1) { std::fprintf(stderr, "moip_b200: node LP does not fit in shared memory (n=%d)\n", dm.n); return MOIP_ERR_LIMIT; }
   long long grid = (long long)num_sms * occ;
   if (grid > b.B) grid = b.B;
   if (grid < 1) grid = 1;
@@ -412,30 +427,33 @@ int launch_fast(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, c
   int ne = 1;                              // restart-test cadence: largest power of two <= norm_every
   while (ne * 2 <= p.norm_every) ne *= 2;
   p.norm_every = ne;
-  k1_fast_kernel<NT, KD, ELLW><<<(unsigned)grid, NT, smem, st>>>(dm, b, p, lpr_log2);
+  kern<<<(unsigned)grid, NT, smem, st>>>(dm, b, p, lpr_log2);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }
 
-template <int NT, int ELLW>
+#ifdef MOIP_K1_EXPERIMENT
+#define MOIP_KD_CASES(NT, E, MB) case 3: return launch_fast<NT, 3, E, MB>(dm, b, p, num_sms, st); case 5: return launch_fast<NT, 5, E, MB>(dm, b, p, num_sms, st);
+#else
+#define MOIP_KD_CASES(NT, E, MB) case 1: return launch_fast<NT, 1, E, MB>(dm, b, p, num_sms, st); case 2: return launch_fast<NT, 2, E, MB>(dm, b, p, num_sms, st); \
+  case 3: return launch_fast<NT, 3, E, MB>(dm, b, p, num_sms, st); case 4: return launch_fast<NT, 4, E, MB>(dm, b, p, num_sms, st); \
+  case 5: return launch_fast<NT, 5, E, MB>(dm, b, p, num_sms, st); case 6: return launch_fast<NT, 6, E, MB>(dm, b, p, num_sms, st);
+#endif
+
+template <int NT, int ELLW, int MINB>
 int launch_kd(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
-  switch (dm.KD) {
-    case 1: return launch_fast<NT, 1, ELLW>(dm, b, p, num_sms, st);
-    case 2: return launch_fast<NT, 2, ELLW>(dm, b, p, num_sms, st);
-    case 3: return launch_fast<NT, 3, ELLW>(dm, b, p, num_sms, st);
-    case 4: return launch_fast<NT, 4, ELLW>(dm, b, p, num_sms, st);
-    case 5: return launch_fast<NT, 5, ELLW>(dm, b, p, num_sms, st);
-    case 6: return launch_fast<NT, 6, ELLW>(dm, b, p, num_sms, st);
-  }
+  switch (dm.KD) { MOIP_KD_CASES(NT, ELLW, MINB) }
   return MOIP_ERR_UNSUPPORTED;
 }
 
-template <int NT>
+template <int NT, int MINB>
 int launch_ell(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   switch (dm.ell2_w) {
-    case 0: return launch_kd<NT, 0>(dm, b, p, num_sms, st);
-    case 1: return launch_kd<NT, 1>(dm, b, p, num_sms, st);
-    case 2: return launch_kd<NT, 2>(dm, b, p, num_sms, st);
+    case 0: return launch_kd<NT, 0, MINB>(dm, b, p, num_sms, st);
+#ifndef MOIP_K1_EXPERIMENT
+    case 1: return launch_kd<NT, 1, MINB>(dm, b, p, num_sms, st);
+#endif
+    case 2: return launch_kd<NT, 2, MINB>(dm, b, p, num_sms, st);
   }
   return MOIP_ERR_UNSUPPORTED;
 }
@@ -445,8 +463,16 @@ int launch_ell(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_
 int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (b.B <= 0) return MOIP_OK;
   MOIP_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(int), st));
-  if (dm.n <= 64 && dm.m <= 32) return launch_ell<32>(dm, b, p, num_sms, st);
-  return launch_ell<128>(dm, b, p, num_sms, st);     // m <= 128 guaranteed by Model::fast_ok
+  if (dm.n <= 64 && dm.m <= 32) return launch_ell<32, 16>(dm, b, p, num_sms, st);
+#ifdef MOIP_K1_EXPERIMENT
+  switch (env_int("MOIP_K1_CFG", 0)) {
+    case 1: return launch_ell<128, 5>(dm, b, p, num_sms, st);
+    case 2: return launch_ell<128, 6>(dm, b, p, num_sms, st);
+    case 3: return launch_ell<256, 2>(dm, b, p, num_sms, st);
+    case 4: return launch_ell<256, 3>(dm, b, p, num_sms, st);
+  }
+#endif
+  return launch_ell<128, 4>(dm, b, p, num_sms, st);     // m <= 128 guaranteed by Model::fast_ok
 }
 
 }  // namespace moip
