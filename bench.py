@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--batch", type=int, default=16384)
     ap.add_argument("--workload", default="ap30", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-fronts", action="store_true")
