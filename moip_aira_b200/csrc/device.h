@@ -62,8 +62,10 @@ struct LpBatch {
   int B;
   const int* cost_idx;        // [B]
   const double* rhs;          // [B][k] objective-bound rows in the model's own sign (+-1e20 free)
-  const int* lb;              // [B][n] integer column bounds of the node
-  const int* ub;
+  int* lb;                    // [B][n] (or [slots][n] with `slot`) integer column bounds of the node;
+  int* ub;                    //        tightened in place when rc_fix is set
+  const int* slot;            // optional indirection: node b lives in row slot[b] of lb/ub/warm_*/out_* (node pool)
+  int rc_fix;                 // reduced-cost bound tightening against the cutoff at node end (fast kernel)
   const double* warm_x;       // [B][n] unscaled warm start or nullptr
   const double* warm_y;       // [B][m]
   double* out_x;              // [B][n] or nullptr
@@ -72,8 +74,8 @@ struct LpBatch {
   double* dual_bound;         // [B] best valid Lagrangian bound seen (min-form)
   int* status;                // [B] MOIP_LP_*
   int* iters;                 // [B]
-  int* branch_var;            // [B] most fractional column or -1
-  double* branch_val;         // [B] its (fractional) value
+  int* branch_var;            // [B][3] the three most fractional columns (-1 = none), best first
+  double* branch_val;         // [B][3] their (fractional) values
   const int* skip;            // [B] nonzero: node already decided by K2, do not solve (or nullptr)
   int cost_stride, rhs_stride;// 0 = all nodes share cost_idx[0] / rhs[0..k)
   const double* cutoff;       // device scalar (min-form); node stops once bound >= *cutoff - cutoff_slack
@@ -87,6 +89,7 @@ struct LpParams {
   int fixed_iters;
   int norm_every;             // restart criteria evaluated every this many iterations
   double cutoff_slack;        // stop when bound >= cutoff - slack (integer objectives: 1 - 1e-6)
+  int int_obj;                // objective is integer valued: stop once ceil(bound) cannot rise any more
 };
 
 int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
@@ -113,6 +116,9 @@ int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queri
               int* which, cudaStream_t st);
 
 // K4
+int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub,
+                    int* xr /*[B][3][n]*/, long long* obj_out /*[B][3][k]*/, unsigned char* feasible_out /*[B][3]*/,
+                    cudaStream_t st);
 int launch_k4(const DevModel& dm, int B, const int* x, const double* rhs, long long* obj_out,
               unsigned char* feasible_out, cudaStream_t st);
 

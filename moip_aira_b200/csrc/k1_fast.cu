@@ -115,6 +115,7 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
       continue;
     }
     // ---------------------------------------------------------------- node load
+    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)node;   // row of the node's arrays
     const int cost = b.cost_idx[(size_t)node * b.cost_stride];
     const double* nrhs = b.rhs + (size_t)node * b.rhs_stride;
     const double inv_dr_cost = 1.0 / dm.dr_k[msS + cost];
@@ -129,9 +130,9 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
       ColRec<ELLW, KD> rc;
       rc.load(crec, j);
       const double idc = 1.0 / dm.dc[j];
-      const double lj = (double)b.lb[(size_t)node * n + j] * idc;
-      const double uj = (double)b.ub[(size_t)node * n + j] * idc;
-      double xj = b.warm_x ? b.warm_x[(size_t)node * n + j] * idc : 0.0;
+      const double lj = (double)b.lb[srow * n + j] * idc;
+      const double uj = (double)b.ub[srow * n + j] * idc;
+      double xj = b.warm_x ? b.warm_x[srow * n + j] * idc : 0.0;
       xj = clampd(xj, lj, uj);
       double* cj_ = col + j * CS;
       cj_[C_XBAR] = xj; cj_[C_XA] = xj; cj_[C_XT] = xj; cj_[C_L] = lj; cj_[C_U] = uj;
@@ -157,7 +158,7 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
         r_idr = 1.0 / dri;
         if (dd >= 0 && dd < k) { r_lo = -HUGE_VAL; r_hi = ((act >> dd) & 1u) ? dm.sgn * nrhs[dd] * dri : HUGE_VAL; }
         else { r_lo = dm.lo_k[row]; r_hi = dm.hi_k[row]; }
-        double yi = b.warm_y ? b.warm_y[(size_t)node * m + row] * r_idr : 0.0;
+        double yi = b.warm_y ? b.warm_y[srow * m + row] * r_idr : 0.0;
         if (r_lo == -HUGE_VAL) yi = dmin(yi, 0.0);
         if (r_hi == HUGE_VAL) yi = dmax(yi, 0.0);
         r_y = yi; r_ya = yi;
@@ -189,7 +190,7 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
     __syncthreads();                       // ysh visible
 
     int kk = 0, it = 0, status = MOIP_LP_ITERLIMIT;
-    double r0sq = 0, rprev = -1.0, best_lb = -HUGE_VAL, pobj = 0;
+    double r0sq = 0, rprev = -1.0, best_lb = -HUGE_VAL, pobj = 0, dobj_last = -HUGE_VAL;
     const int iter_cap = p.fixed_iters > 0 ? p.fixed_iters : p.max_iter;
     int next_check = p.fixed_iters > 0 ? 0x7fffffff : p.check_every;
 
@@ -323,6 +324,7 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
         bsum<4, NT>(aC, redC, tid);
         pobj = aC[0];
         const double dobj = aC[1] + aC[2];
+        dobj_last = dobj;
         if (p.fixed_iters > 0) best_lb = dobj;
         else {
           if (dobj > best_lb) best_lb = dobj;
@@ -332,6 +334,9 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
           if (best_lb >= cutoff - p.cutoff_slack) { status = MOIP_LP_CUTOFF; stop = true; }
           else if (best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
           else if (rel <= p.eps) { status = MOIP_LP_CONVERGED; stop = true; }
+          else if (p.int_obj && sqrt(aC[3]) * kkt_binv <= 1e-5 && ceil(best_lb - 1e-6) >= ceil(pobj - 1e-3)) {
+            status = MOIP_LP_CONVERGED; stop = true;      // the integer-rounded bound cannot improve any further
+          }
         }
       }
       if (stop) break;
@@ -356,31 +361,69 @@ k1_fast_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int l
     }
 
     // ---------------------------------------------------------------- node store
-    double bestf = -1.0; int bestj = -1;
-    for (int j = tid; j < n; j += NT) {
-      const double v = col[j * CS + C_XT] * dm.dc[j];
-      if (b.out_x) b.out_x[(size_t)node * n + j] = v;
-      const double f = fabs(v - rint(v));
-      if (f > bestf) { bestf = f; bestj = j; }
-    }
-    if (b.out_y && leader) b.out_y[(size_t)node * m + row] = (live ? r_yt : 0.0) * dm.dr_k[row];
-    if (b.branch_var) {
+    // Reduced-cost tightening: with the Lagrangian bound L(yt) = dobj_last and reduced costs r, any
+    // point with x_j >= l_j + t has objective >= L + r_j t (r_j > 0), so columns can be tightened against
+    // the cutoff (strictly better integer solutions have objective <= cutoff - slack).  Valid for any yt.
+    if (b.rc_fix && b.cutoff && status != MOIP_LP_CUTOFF && status != MOIP_LP_INFEASIBLE) {
+      const double cutoff = *((volatile const double*)b.cutoff);
+      const double room = cutoff - p.cutoff_slack - dobj_last;
+      if (cutoff < HUGE_VAL && room >= 0.0 && dobj_last > -HUGE_VAL) {
+        double ytd[KD];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double of = __shfl_xor_sync(0xffffffffu, bestf, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
-        if (of > bestf || (of == bestf && oj >= 0 && (bestj < 0 || oj < bestj))) { bestf = of; bestj = oj; }
+        for (int d = 0; d < KD; ++d) ytd[d] = ((act >> d) & 1u) ? ytsh[msS + d] : 0.0;
+        for (int j = tid; j < n; j += NT) {
+          ColRec<ELLW, KD> rc;
+          rc.load(crec, j);
+          double g = 0, cj = 0;
+#pragma unroll
+          for (int e = 0; e < ELLW; ++e) g = fma(rc.ell(e), ytsh[rc.row(e)], g);
+#pragma unroll
+          for (int d = 0; d < KD; ++d) { g = fma(rc.dense(d), ytd[d], g); if (d == cost) cj = rc.dense(d); }
+          const double r = (cj * inv_dr_cost - g) / dm.dc[j];        // unscaled reduced cost
+          int lbj = b.lb[srow * n + j], ubj = b.ub[srow * n + j];
+          if (lbj < ubj) {
+            if (r > 1e-9) {
+              const double t = floor(room / r + 1e-9);
+              if (t < (double)(ubj - lbj)) { ubj = lbj + (int)t; b.ub[srow * n + j] = ubj; }
+            } else if (r < -1e-9) {
+              const double t = floor(room / (-r) + 1e-9);
+              if (t < (double)(ubj - lbj)) { lbj = ubj - (int)t; b.lb[srow * n + j] = lbj; }
+            }
+          }
+        }
       }
-      __syncthreads();
-      if (lane == 0) { redA[warp * 2] = bestf; redA[warp * 2 + 1] = (double)bestj; }
-      __syncthreads();
-      if (tid == 0) {
-        for (int wq = 1; wq < NW; ++wq) {
+    }
+    if (b.out_x)
+      for (int j = tid; j < n; j += NT) b.out_x[srow * n + j] = col[j * CS + C_XT] * dm.dc[j];
+    if (b.out_y && leader) b.out_y[srow * m + row] = (live ? r_yt : 0.0) * dm.dr_k[row];
+    if (b.branch_var) {           // the three most fractional columns, best first
+      int c0 = -1, c1 = -1;
+      for (int r = 0; r < 3; ++r) {
+        double bestf = -1.0; int bestj = -1;
+        for (int j = tid; j < n; j += NT) {
+          const double v = col[j * CS + C_XT] * dm.dc[j];
+          const double f = fabs(v - rint(v));
+          if (j != c0 && j != c1 && f > bestf) { bestf = f; bestj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double of = __shfl_xor_sync(0xffffffffu, bestf, o);
+          const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+          if (of > bestf || (of == bestf && oj >= 0 && (bestj < 0 || oj < bestj))) { bestf = of; bestj = oj; }
+        }
+        __syncthreads();
+        if (lane == 0) { redA[warp * 2] = bestf; redA[warp * 2 + 1] = (double)bestj; }
+        __syncthreads();
+        for (int wq = 0; wq < NW; ++wq) {     // every thread folds the warp results: uniform outcome
           const double of = redA[wq * 2]; const int oj = (int)redA[wq * 2 + 1];
           if (of > bestf || (of == bestf && oj >= 0 && (bestj < 0 || oj < bestj))) { bestf = of; bestj = oj; }
         }
-        b.branch_var[node] = (bestf > 1e-6) ? bestj : -1;
-        if (b.branch_val) b.branch_val[node] = (bestj >= 0) ? col[bestj * CS + C_XT] * dm.dc[bestj] : 0.0;
+        const int pick = (bestf > 1e-6) ? bestj : -1;
+        if (tid == 0) {
+          b.branch_var[(size_t)node * 3 + r] = pick;
+          if (b.branch_val) b.branch_val[(size_t)node * 3 + r] = (pick >= 0) ? col[pick * CS + C_XT] * dm.dc[pick] : 0.0;
+        }
+        if (r == 0) c0 = pick; else c1 = pick;
       }
     }
     if (tid == 0) {

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
     }
 
     // ---------------------------------------------------------------- node load
+    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)node;   // row of the node's arrays
     const int cost = b.cost_idx[(size_t)node * b.cost_stride];
     const double* nrhs = b.rhs + (size_t)node * b.rhs_stride;
     const double inv_dr_cost = 1.0 / dm.dr[ms + cost];
@@ -104,9 +105,9 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
     double a0[6] = {0, 0, 0, 0, 0, 0};  // |c|^2, obj_upper, D.x per objective row
     for (int j = tid; j < n; j += NT) {
       const double idc = 1.0 / dm.dc[j];
-      const double lj = (double)b.lb[(size_t)node * n + j] * idc;
-      const double uj = (double)b.ub[(size_t)node * n + j] * idc;
-      double xj = b.warm_x ? b.warm_x[(size_t)node * n + j] * idc : 0.0;
+      const double lj = (double)b.lb[srow * n + j] * idc;
+      const double uj = (double)b.ub[srow * n + j] * idc;
+      double xj = b.warm_x ? b.warm_x[srow * n + j] * idc : 0.0;
       xj = clampd(xj, lj, uj);
       l[j] = lj; u[j] = uj; x[j] = xj; xa[j] = xj;
       const double cj = Dc[j] * inv_dr_cost;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
         loi = -HUGE_VAL;
         hii = ((act >> o) & 1u) ? dm.sgn * nrhs[o] * dm.dr[i] : HUGE_VAL;
       }
-      double yi = b.warm_y ? b.warm_y[(size_t)node * m + i] / dm.dr[i] : 0.0;
+      double yi = b.warm_y ? b.warm_y[srow * m + i] / dm.dr[i] : 0.0;
       if (loi == -HUGE_VAL) yi = fmin(yi, 0.0);
       if (hii == HUGE_VAL) yi = fmax(yi, 0.0);
       lo[i] = loi; hi[i] = hii; y[i] = yi; ya[i] = yi;
@@ -314,12 +315,12 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
     double bestf = -1.0; int bestj = -1;
     for (int j = tid; j < n; j += NT) {
       const double v = 0.5 * (xbar[j] + x[j]) * dm.dc[j];
-      if (b.out_x) b.out_x[(size_t)node * n + j] = v;
+      if (b.out_x) b.out_x[srow * n + j] = v;
       const double f = fabs(v - rint(v));
       if (f > bestf) { bestf = f; bestj = j; }
     }
     if (b.out_y)
-      for (int i = tid; i < m; i += NT) b.out_y[(size_t)node * m + i] = yt[i] * dm.dr[i];
+      for (int i = tid; i < m; i += NT) b.out_y[srow * m + i] = yt[i] * dm.dr[i];
     if (b.branch_var) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -335,8 +336,9 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
           const double of = redA[wq * 2]; const int oj = (int)redA[wq * 2 + 1];
           if (of > bestf || (of == bestf && oj >= 0 && (bestj < 0 || oj < bestj))) { bestf = of; bestj = oj; }
         }
-        b.branch_var[node] = (bestf > 1e-6) ? bestj : -1;
-        if (b.branch_val) b.branch_val[node] = (bestj >= 0) ? 0.5 * (xbar[bestj] + x[bestj]) * dm.dc[bestj] : 0.0;
+        b.branch_var[(size_t)node * 3] = (bestf > 1e-6) ? bestj : -1;
+        b.branch_var[(size_t)node * 3 + 1] = -1; b.branch_var[(size_t)node * 3 + 2] = -1;
+        if (b.branch_val) b.branch_val[(size_t)node * 3] = (bestj >= 0) ? 0.5 * (xbar[bestj] + x[bestj]) * dm.dc[bestj] : 0.0;
       }
     }
     if (tid == 0) {

@@ -153,7 +153,9 @@ __global__ void __launch_bounds__(128) k2_branch_kernel(const DevModel dm, const
     int* dub = pool.ub + (size_t)op.child * n;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
       int a = slb[j], b2 = sub[j];
-      if (j == op.var) { a = max(a, op.new_lb); b2 = min(b2, op.new_ub); }
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (q < op.nv && j == op.var[q]) { a = max(a, op.new_lb[q]); b2 = min(b2, op.new_ub[q]); }
       dlb[j] = a; dub[j] = b2;
     }
     const double* sx = pool.wx + (size_t)op.parent * n;

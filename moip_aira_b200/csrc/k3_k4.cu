@@ -111,7 +111,57 @@ __global__ void __launch_bounds__(128) k4_verify_kernel(const DevModel dm, int B
   }
 }
 
+// Rounds a node's LP point three ways (nearest / down / up, clipped to the node's bounds) and verifies
+// each candidate exactly; one warp per (node, candidate).  Feeds the incumbent search of the B&B.
+__global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm, int B, const int* slot, const double* wx,
+                                                              const int* lb, const int* ub, int* xr, long long* obj_out,
+                                                              unsigned char* feasible_out) {
+  const int lane = threadIdx.x & 31;
+  const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n = dm.n;
+  for (int w = wglobal; w < B * 3; w += nwarps) {
+    const int node = w / 3, mode = w - node * 3;
+    const size_t srow = slot ? (size_t)slot[node] : (size_t)node;
+    int* xp = xr + (size_t)w * n;
+    long long obj[MOIP_MAX_OBJ] = {0, 0, 0, 0};
+    for (int j = lane; j < n; j += 32) {
+      const double v = wx[srow * n + j];
+      int r = mode == 0 ? (int)llrint(v) : mode == 1 ? (int)floor(v + 1e-6) : (int)ceil(v - 1e-6);
+      r = max(lb[srow * n + j], min(ub[srow * n + j], r));
+      xp[j] = r;
+#pragma unroll
+      for (int o = 0; o < MOIP_MAX_OBJ; ++o)
+        if (o < dm.k) obj[o] += dm.ci[(size_t)o * n + j] * (long long)r;
+    }
+#pragma unroll
+    for (int o = 0; o < MOIP_MAX_OBJ; ++o) obj[o] = warp_sum_ll(obj[o]);
+    __syncwarp();
+    int bad = 0;
+    for (int i = 0; i < dm.ms; ++i) {
+      long long a = 0;
+      for (int e = dm.s_ptr[i] + lane; e < dm.s_ptr[i + 1]; e += 32) a += dm.ai_val[e] * (long long)xp[dm.s_col[e]];
+      a = warp_sum_ll(a);
+      if (a < dm.ri_lo[i] || a > dm.ri_hi[i]) bad = 1;
+    }
+    if (lane == 0) {
+      feasible_out[w] = bad ? 0 : 1;
+      for (int o = 0; o < dm.k; ++o) obj_out[(size_t)w * dm.k + o] = obj[o];
+    }
+  }
+}
+
 }  // namespace
+
+int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub, int* xr,
+                    long long* obj_out, unsigned char* feasible_out, cudaStream_t st) {
+  if (B <= 0) return MOIP_OK;
+  int blocks = (B * 3 + 3) / 4;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out);
+  MOIP_CUDA(cudaGetLastError());
+  return MOIP_OK;
+}
 
 int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queries, int sense, int* first_match,
               int* which, cudaStream_t st) {

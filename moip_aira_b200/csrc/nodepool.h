@@ -12,8 +12,9 @@ struct PoolView {
   double* wy;   // [slots][m]
 };
 
-struct BranchOp {
-  int parent, child, var, new_lb, new_ub;
+struct BranchOp {           // child = copy of parent with up to 3 columns tightened
+  int parent, child, nv;
+  int var[3], new_lb[3], new_ub[3];
 };
 
 int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const int* ids, const long long* obj_lo,

@@ -111,6 +111,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->bb_eps = env_double("MOIP_BB_EPS", 1e-5);
   c->bb_check = env_int("MOIP_BB_CHECK", 32);
   c->norm_every = env_int("MOIP_NORM_EVERY", 4);
+  c->bb_levels = env_int("MOIP_BB_LEVELS", 3);
   *out = c;
   return MOIP_OK;
 }
@@ -166,7 +167,7 @@ extern "C" int moip_lp_batch_upload(moip_ctx* c, int B, const int* cost_idx, con
   int rc = 0;
   rc |= c->b_cost.ensure(B); rc |= c->b_rhs.ensure((size_t)B * d.k); rc |= c->b_masks.ensure((size_t)B * words);
   rc |= c->b_lb.ensure((size_t)B * d.n); rc |= c->b_ub.ensure((size_t)B * d.n);
-  rc |= c->b_status.ensure(B); rc |= c->b_iters.ensure(B); rc |= c->b_branch.ensure(B);
+  rc |= c->b_status.ensure(B); rc |= c->b_iters.ensure(B); rc |= c->b_branch.ensure((size_t)3 * B);
   rc |= c->b_pobj.ensure(B); rc |= c->b_dbound.ensure(B); rc |= c->b_x.ensure((size_t)B * d.n);
   rc |= c->b_counter.ensure(1); rc |= c->b_cutoff.ensure(1);
   if (rc) return MOIP_ERR_CUDA;
@@ -197,13 +198,13 @@ extern "C" int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params) {
   b.cost_idx = c->b_cost.p; b.rhs = c->b_rhs.p; b.lb = c->b_lb.p; b.ub = c->b_ub.p;
   b.warm_x = nullptr; b.warm_y = nullptr; b.out_x = c->b_x.p; b.out_y = nullptr;
   b.primal_obj = c->b_pobj.p; b.dual_bound = c->b_dbound.p; b.status = c->b_status.p; b.iters = c->b_iters.p;
-  b.branch_var = c->b_branch.p; b.branch_val = nullptr; b.skip = nullptr;
+  b.branch_var = c->b_branch.p; b.branch_val = nullptr; b.skip = nullptr; b.slot = nullptr; b.rc_fix = 0;
   b.cost_stride = 1; b.rhs_stride = d.k;
   b.cutoff = c->b_cutoff.p; b.work_counter = c->b_counter.p;
   LpParams p{};
   p.eps = dp.eps; p.max_iter = dp.max_iter; p.check_every = dp.check_every > 0 ? dp.check_every : 32;
   p.fixed_iters = dp.fixed_iters; p.norm_every = c->norm_every > 0 ? c->norm_every : 1;
-  p.cutoff_slack = 0.0;
+  p.cutoff_slack = 0.0; p.int_obj = 0;
   c->stats.kernel_launches += 1;
   c->stats.node_lps += b.B;
   return d.fast_ok ? launch_k1_fast(d, b, p, c->num_sms, c->stream) : launch_k1(d, b, p, c->num_sms, c->stream);
@@ -401,6 +402,7 @@ struct OpenNode {
   int slot;
   double bound;   // min-form valid lower bound inherited from the parent
   int depth;
+  int pref;       // how many branched columns went to the side nearer to the parent's LP value
 };
 }  // namespace
 
@@ -433,22 +435,22 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     have_inc = true; inc_val = (long long)sgn * v; inc_x = *inc_x_in;
   }
   // batch geometry
-  int Bmax = bb_batch > 0 ? bb_batch : num_sms * 4;
+  int Bmax = bb_batch > 0 ? bb_batch : num_sms * (dm.n <= 64 ? 16 : 4);
   if (ensure_pool(std::max(256, 4 * Bmax))) return MOIP_ERR_CUDA;
   int rc = 0;
   rc |= r_ids.ensure((size_t)Bmax + 1); rc |= r_flag.ensure(Bmax); rc |= r_lb.ensure((size_t)Bmax * n); rc |= r_ub.ensure((size_t)Bmax * n);
-  rc |= r_status.ensure(Bmax); rc |= r_iters.ensure(Bmax); rc |= r_branch.ensure(Bmax); rc |= r_xr.ensure((size_t)Bmax * n);
+  rc |= r_status.ensure(Bmax); rc |= r_iters.ensure(Bmax); rc |= r_branch.ensure((size_t)3 * Bmax); rc |= r_xr.ensure((size_t)Bmax * 3 * n);
   rc |= r_counter.ensure(1); rc |= r_wx.ensure((size_t)Bmax * n); rc |= r_wy.ensure((size_t)Bmax * m);
   rc |= r_x.ensure((size_t)Bmax * n); rc |= r_y.ensure((size_t)Bmax * m); rc |= r_pobj.ensure(Bmax); rc |= r_dbound.ensure(Bmax);
-  rc |= r_bval.ensure(Bmax); rc |= r_rhs.ensure(k); rc |= r_cutoff.ensure(1); rc |= r_leaf.ensure((size_t)Bmax * k);
-  rc |= r_olo.ensure(k); rc |= r_ohi.ensure(k); rc |= r_cobj.ensure((size_t)Bmax * k); rc |= r_cfeas.ensure(Bmax);
-  rc |= r_ops.ensure((size_t)2 * Bmax);
+  rc |= r_bval.ensure((size_t)3 * Bmax); rc |= r_rhs.ensure(k); rc |= r_cutoff.ensure(1); rc |= r_leaf.ensure((size_t)Bmax * k);
+  rc |= r_olo.ensure(k); rc |= r_ohi.ensure(k); rc |= r_cobj.ensure((size_t)Bmax * 3 * k); rc |= r_cfeas.ensure((size_t)Bmax * 3);
+  rc |= r_ops.ensure((size_t)8 * Bmax);
   // packed D2H layout per round
   const size_t off_flag = 0, off_status = off_flag + sizeof(int) * Bmax, off_iters = off_status + sizeof(int) * Bmax,
-               off_branch = off_iters + sizeof(int) * Bmax, off_dbound = off_branch + sizeof(int) * Bmax,
-               off_bval = off_dbound + sizeof(double) * Bmax, off_leaf = off_bval + sizeof(double) * Bmax,
-               off_cobj = off_leaf + sizeof(long long) * Bmax * k, off_cfeas = off_cobj + sizeof(long long) * Bmax * k,
-               off_end = off_cfeas + Bmax;
+               off_branch = off_iters + sizeof(int) * Bmax, off_dbound = off_branch + sizeof(int) * 3 * Bmax + 8,
+               off_bval = off_dbound + sizeof(double) * Bmax, off_leaf = off_bval + sizeof(double) * 3 * Bmax,
+               off_cobj = off_leaf + sizeof(long long) * Bmax * k, off_cfeas = off_cobj + sizeof(long long) * Bmax * 3 * k,
+               off_end = off_cfeas + (size_t)Bmax * 3;
   rc |= h_round.ensure(off_end + 64);
   if (rc) return MOIP_ERR_CUDA;
   PoolView pool{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
@@ -471,7 +473,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       MOIP_CUDA(cudaMemsetAsync(pool.wx + (size_t)s * n, 0, sizeof(double) * n, stream));
       MOIP_CUDA(cudaMemsetAsync(pool.wy + (size_t)s * m, 0, sizeof(double) * m, stream));
     }
-    open.push_back({s, -HUGE_VAL, 0});
+    open.push_back({s, -HUGE_VAL, 0, 0});
   }
   std::vector<int> ids;
   std::vector<OpenNode> batch;
@@ -480,7 +482,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   bool first_round = true;
   LpParams lp{};
   lp.eps = bb_eps; lp.max_iter = bb_max_iter; lp.check_every = bb_check; lp.fixed_iters = 0;
-  lp.norm_every = norm_every > 0 ? norm_every : 1; lp.cutoff_slack = 1.0 - 1e-6;
+  lp.norm_every = norm_every > 0 ? norm_every : 1; lp.cutoff_slack = 1.0 - 1e-6; lp.int_obj = 1;
 
   auto prunable = [&](double bound) {
     return have_inc && bound > -HUGE_VAL && std::ceil(bound - 1e-6) >= (double)inc_val;
@@ -496,6 +498,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     else
       std::sort(open.begin(), open.end(), [](const OpenNode& a, const OpenNode& b) {
         if (a.depth != b.depth) return a.depth < b.depth;      // deepest at the back
+        if (a.pref != b.pref) return a.pref < b.pref;
         return a.bound > b.bound;
       });
     batch.clear(); ids.clear();
@@ -522,28 +525,26 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     MOIP_CUDA(cudaMemcpyAsync(r_cutoff.p, &cut, sizeof(double), cudaMemcpyHostToDevice, stream));
     // (the H2D sources above are host vectors/locals that stay alive until the sync below)
     if (launch_k2_propagate(dm, pool, B, r_ids.p, r_olo.p, r_ohi.p, 16, r_flag.p, r_leaf.p, stream)) return MOIP_ERR_CUDA;
-    if (launch_k2_gather(dm, pool, B, r_ids.p, r_lb.p, r_ub.p, r_wx.p, r_wy.p, stream)) return MOIP_ERR_CUDA;
     LpBatch b{};
-    b.B = B; b.cost_idx = nullptr; b.rhs = r_rhs.p; b.lb = r_lb.p; b.ub = r_ub.p;
-    b.warm_x = r_wx.p; b.warm_y = r_wy.p; b.out_x = r_x.p; b.out_y = r_y.p;
+    b.B = B; b.rhs = r_rhs.p; b.lb = pool.lb; b.ub = pool.ub; b.slot = r_ids.p; b.rc_fix = have_inc ? 1 : 0;
+    b.warm_x = pool.wx; b.warm_y = pool.wy; b.out_x = pool.wx; b.out_y = pool.wy;   // iterate returns to the node's slot
     b.primal_obj = r_pobj.p; b.dual_bound = r_dbound.p; b.status = r_status.p; b.iters = r_iters.p;
     b.branch_var = r_branch.p; b.branch_val = r_bval.p; b.skip = r_flag.p;
     b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = r_cutoff.p; b.work_counter = r_counter.p;
     b.cost_idx = r_ids.p + Bmax;   // one shared cost index, staged behind the ids (cost_stride = 0)
     if (dm.fast_ok ? launch_k1_fast(dm, b, lp, num_sms, stream) : launch_k1(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
-    if (launch_k2_scatter_round(dm, pool, B, r_ids.p, r_x.p, r_y.p, r_xr.p, stream)) return MOIP_ERR_CUDA;
-    if (launch_k4(dm, B, r_xr.p, nullptr, r_cobj.p, r_cfeas.p, stream)) return MOIP_ERR_CUDA;
-    stats.kernel_launches += 5;
+    if (launch_k4_round(dm, B, r_ids.p, pool.wx, pool.lb, pool.ub, r_xr.p, r_cobj.p, r_cfeas.p, stream)) return MOIP_ERR_CUDA;
+    stats.kernel_launches += 3;
     unsigned char* H = h_round.p;
     MOIP_CUDA(cudaMemcpyAsync(H + off_flag, r_flag.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
     MOIP_CUDA(cudaMemcpyAsync(H + off_status, r_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
     MOIP_CUDA(cudaMemcpyAsync(H + off_iters, r_iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_branch, r_branch.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_branch, r_branch.p, sizeof(int) * 3 * B, cudaMemcpyDeviceToHost, stream));
     MOIP_CUDA(cudaMemcpyAsync(H + off_dbound, r_dbound.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_bval, r_bval.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_bval, r_bval.p, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, stream));
     MOIP_CUDA(cudaMemcpyAsync(H + off_leaf, r_leaf.p, sizeof(long long) * B * k, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_cobj, r_cobj.p, sizeof(long long) * B * k, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_cfeas, r_cfeas.p, (size_t)B, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_cobj, r_cobj.p, sizeof(long long) * B * 3 * k, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H + off_cfeas, r_cfeas.p, (size_t)B * 3, cudaMemcpyDeviceToHost, stream));
     MOIP_CUDA(cudaStreamSynchronize(stream));
     const int* flag = (const int*)(H + off_flag);
     const int* status = (const int*)(H + off_status);
@@ -561,35 +562,42 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       for (int o = 0; o < k; ++o) if (ov[o] < olo[o] || ov[o] > ohi[o]) return false;
       return true;
     };
+    std::vector<long long> node_cand(B, LLONG_MAX);   // best verified rounding of each node (min-form), if any
     for (int i = 0; i < B; ++i) {
       if (flag[i] == 2) {
         const long long v = (long long)sgn * leaf[(size_t)i * k + cost];
-        if (v < best_val) { best_val = v; best_src = i; best_is_leaf = true; }
+        if (v < best_val) { best_val = v; best_src = i * 3; best_is_leaf = true; }
       } else if (flag[i] == 0) {
         stats.node_lps += 1;
         stats.lp_iterations += iters[i];
-        if (cfeas[i] && within(cobj + (size_t)i * k)) {
-          const long long v = (long long)sgn * cobj[(size_t)i * k + cost];
-          if (v < best_val) { best_val = v; best_src = i; best_is_leaf = false; }
+        for (int c3 = 0; c3 < 3; ++c3) {
+          const size_t w3 = (size_t)i * 3 + c3;
+          if (cfeas[w3] && within(cobj + w3 * k)) {
+            const long long v = (long long)sgn * cobj[w3 * k + cost];
+            if (v < node_cand[i]) node_cand[i] = v;
+            if (v < best_val) { best_val = v; best_src = (int)w3; best_is_leaf = false; }
+          }
         }
       }
     }
     if (best_src >= 0) {
       inc_x.resize(n);
-      const int* src = best_is_leaf ? pool.lb + (size_t)ids[best_src] * n : r_xr.p + (size_t)best_src * n;
+      const int* src = best_is_leaf ? pool.lb + (size_t)ids[best_src / 3] * n : r_xr.p + (size_t)best_src * n;
       MOIP_CUDA(cudaMemcpyAsync(inc_x.data(), src, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
       MOIP_CUDA(cudaStreamSynchronize(stream));
       inc_val = best_val; have_inc = true;
     }
     if (first_round && flag[0] == 0) {   // remember the root iterate as warm start for the next IP on this objective
       root_x[cost].resize(n); root_y[cost].resize(m);
-      MOIP_CUDA(cudaMemcpyAsync(root_x[cost].data(), r_x.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
-      MOIP_CUDA(cudaMemcpyAsync(root_y[cost].data(), r_y.p, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaMemcpyAsync(root_x[cost].data(), pool.wx + (size_t)ids[0] * n, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaMemcpyAsync(root_y[cost].data(), pool.wy + (size_t)ids[0] * m, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
       MOIP_CUDA(cudaStreamSynchronize(stream));
     }
     first_round = false;
-    // ---- branch
+    // ---- branch.  While the device is under-filled the tree is expanded several levels per round
+    // (children over the 2 or 3 most fractional columns at once): rounds are latency-bound, idle SMs are free.
     ops.clear(); to_free.clear();
+    std::vector<int> todo;
     for (int i = 0; i < B; ++i) {
       const OpenNode& nd = batch[i];
       to_free.push_back(nd.slot);
@@ -597,34 +605,46 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       if (status[i] == MOIP_LP_CUTOFF || status[i] == MOIP_LP_INFEASIBLE) continue;
       const double lbnd = std::max(nd.bound, dbound[i]);
       if (prunable(lbnd)) continue;
-      int var = branch[i];
-      double val = bval[i];
-      if (var < 0) {
-        // LP point is integral.  If its rounding is feasible and attains ceil(bound) the node is solved.
-        if (cfeas[i] && within(cobj + (size_t)i * k) &&
-            (double)((long long)sgn * cobj[(size_t)i * k + cost]) <= std::ceil(lbnd - 1e-6)) continue;
-        var = -2;   // pick the first unfixed column on the host side (needs the node's bounds)
-      }
-      if (var == -2) {
-        // rare path: fetch the node's bounds and branch on the first unfixed column at its midpoint
+      if (branch[3 * i] < 0 && node_cand[i] != LLONG_MAX && (double)node_cand[i] <= std::ceil(lbnd - 1e-6)) continue;   // solved by its rounding
+      todo.push_back(i);
+    }
+    int levels = 1;
+    if (bb_levels > 1) {
+      while (levels < bb_levels && (long long)todo.size() * (2LL << levels) + (long long)open.size() <= (long long)Bmax) ++levels;
+    }
+    for (int i : todo) {
+      const OpenNode& nd = batch[i];
+      const double lbnd = std::max(nd.bound, dbound[i]);
+      int vars[3]; double vals[3]; int nv = 0;
+      for (int q = 0; q < levels; ++q) if (branch[3 * i + q] >= 0) { vars[nv] = branch[3 * i + q]; vals[nv] = bval[3 * i + q]; ++nv; }
+      if (nv == 0) {
+        // LP point integral but not accepted: branch on the first unfixed column at its midpoint (rare path)
         std::vector<int> nlb(n), nub(n);
         MOIP_CUDA(cudaMemcpyAsync(nlb.data(), pool.lb + (size_t)nd.slot * n, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
         MOIP_CUDA(cudaMemcpyAsync(nub.data(), pool.ub + (size_t)nd.slot * n, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
         MOIP_CUDA(cudaStreamSynchronize(stream));
-        var = -1;
-        for (int j = 0; j < n; ++j) if (nlb[j] < nub[j]) { var = j; val = 0.5 * ((double)nlb[j] + (double)nub[j]); break; }
-        if (var < 0) continue;   // fully fixed: K2 will have classified it as a leaf
+        for (int j = 0; j < n; ++j) if (nlb[j] < nub[j]) { vars[0] = j; vals[0] = 0.5 * ((double)nlb[j] + (double)nub[j]); nv = 1; break; }
+        if (nv == 0) continue;   // fully fixed: K2 will have classified it as a leaf
       }
-      const int fl = (int)std::floor(val);
-      const int c0 = alloc_slot(), c1 = alloc_slot();
-      if (c0 < 0 || c1 < 0) return MOIP_ERR_CUDA;
-      pool = PoolView{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
-      ops.push_back({nd.slot, c0, var, INT_MIN, fl});
-      ops.push_back({nd.slot, c1, var, fl + 1, INT_MAX});
-      // the child closer to the LP value is explored first when diving (pushed last)
-      const bool up_first = (val - fl) >= 0.5;
-      OpenNode a{c0, lbnd, nd.depth + 1}, bnode{c1, lbnd, nd.depth + 1};
-      if (up_first) { open.push_back(a); open.push_back(bnode); } else { open.push_back(bnode); open.push_back(a); }
+      const int nchild = 1 << nv;
+      for (int cmb = 0; cmb < nchild; ++cmb) {
+        const int cs = alloc_slot();
+        if (cs < 0) return MOIP_ERR_CUDA;
+        pool = PoolView{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
+        BranchOp op{};
+        op.parent = nd.slot; op.child = cs; op.nv = nv;
+        int closeness = 0;      // how many columns go to the side nearer to the LP value (explored first when diving)
+        for (int q = 0; q < nv; ++q) {
+          const int fl = (int)std::floor(vals[q]);
+          const bool up = (cmb >> q) & 1;
+          op.var[q] = vars[q];
+          op.new_lb[q] = up ? fl + 1 : INT_MIN;
+          op.new_ub[q] = up ? INT_MAX : fl;
+          if (up == ((vals[q] - fl) >= 0.5)) ++closeness;
+        }
+        ops.push_back(op);
+        open.push_back({cs, lbnd, nd.depth + nv, closeness});
+      }
     }
     if (!ops.empty()) {
       MOIP_CUDA(cudaMemcpyAsync(r_ops.p, ops.data(), sizeof(BranchOp) * ops.size(), cudaMemcpyHostToDevice, stream));

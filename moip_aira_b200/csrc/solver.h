@@ -110,6 +110,7 @@ struct moip_ctx {
   double bb_eps = 1e-5;
   int bb_check = 32;
   int norm_every = 1;
+  int bb_levels = 3;           // max tree levels expanded per round while the device is under-filled
 
   int ensure_pool(int slots);
   int alloc_slot();
