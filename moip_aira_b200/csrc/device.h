@@ -45,6 +45,8 @@ struct DevModel {
   int col_units;
   const double* colrec;       // [n][col_units] packed column records (see model.h)
   const double* rowrec;       // [RW][msS][2]   packed row-ELL entries
+  int reg_ok, RWP, reg_lpr_log2, reg_trips;   // register-resident kernel image (k1_reg.cuh)
+  const double* colrec2;      // [n][col_units] ids packed as (product byte offset << 16 | dual byte offset)
   const double* dr_k;         // [m]
   const double* lo_k;         // [m] scaled structural bounds in kernel order
   const double* hi_k;
@@ -92,6 +94,8 @@ struct LpParams {
   int int_obj;                // objective is integer valued: stop once ceil(bound) cannot rise any more
 };
 
+int launch_k1_any(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);   // best path the model allows
+int launch_k1_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_expand_masks(const DevModel& dm, int B, const uint32_t* masks, int mask_words, int* lb, int* ub,

@@ -1,0 +1,634 @@
+// K1 (register-resident path) -- batched node-LP relaxations, one CTA per B&B node, reflected
+// restarted Halpern PDHG in fp64.  Same mathematics as k1_fast.cu / k1_pdhg.cu; what changes is
+// where the data lives.  The ncu profile of k1_fast (profiles/r01_k1_v3_summary.md) showed the SM's
+// L1/shared data pipe at 76 % of peak: ~1 410 wavefronts per node-iteration, of which 337 re-read the
+// packed column records, 337 moved the column state through shared memory and ~600 belonged to the
+// row-ELL pass (record loads + gathers of xbar).  Here
+//   * every thread owns CPT columns (j = tid + c*NT) for the whole life of the CTA: their packed model
+//     records are loaded ONCE per CTA into registers, and the column state (reflected point, anchor,
+//     PDHG point) never leaves registers; only the box {l,u} sits in a thread-private shared slot;
+//   * S*xbar of the short rows is formed from per-entry products that the column pass scatters into
+//     prod[row*RWP + pos] (position chosen on the host so that a half-warp's stores and the row
+//     owners' loads fall in distinct banks); the row owners (LPR lanes per row) just add them up --
+//     no row records, no gathers;
+//   * the dense rows (objective-bound rows, long structural rows) and the two restart norms are NOT
+//     reduced with warp shuffles in the column pass (that was ~100 of 570 instructions per thread and
+//     iteration): every thread stores its partial sums to part[v][tid] and one half-warp per dense row
+//     adds them up in the row phase, in parallel with the short-row owners;
+//   * the objective is folded into the dual of its own dense row (y_cost - 1/dr_cost), so the reduced
+//     cost needs no separate cost term;
+//   * duals and product slots are addressed through 16-bit absolute shared-memory addresses packed in the
+//     column record (ld.shared / st.shared on a register address, no pointer arithmetic).
+// Per node-iteration the shared-memory traffic drops to: 2 y loads + 2 product stores + {l,u}, anchor load
+// and xt store per column, one product load per nonzero, KD(+2) partial sums per thread.
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+
+#include "device.h"
+
+namespace moip {
+namespace k1reg {
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NV, int NT>
+__device__ __forceinline__ void bsum(double (&v)[NV], double* red, int tid) {
+  constexpr int NW = NT / 32;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = wsum(v[i]);
+  if (NW == 1) { __syncthreads(); return; }
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[(tid >> 5) * NV + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w * NV + i];
+    v[i] = s;
+  }
+}
+
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }
+__device__ __forceinline__ double clampd(double v, double a, double b) { return dmin(dmax(v, a), b); }
+
+// One column's share of the model: ELLW short-row values | KD dense-row values | ELLW packed ids,
+// id = (byte offset of the product slot << 16) | byte offset of the row's dual in ysh.
+template <int ELLW, int KD>
+struct ColRec {
+  static constexpr int UC = ELLW + KD + (ELLW + 1) / 2;
+  static constexpr int UP = (UC + 1) & ~1;
+  double u[UP];
+  __device__ __forceinline__ void load(const double* __restrict__ base, int j) {
+    const double2* p = reinterpret_cast<const double2*>(base) + (size_t)j * (UP / 2);
+#pragma unroll
+    for (int q = 0; q < UP / 2; ++q) { const double2 t = __ldg(p + q); u[2 * q] = t.x; u[2 * q + 1] = t.y; }
+  }
+  __device__ __forceinline__ void clear(unsigned dummy_id) {
+#pragma unroll
+    for (int q = 0; q < UP; ++q) u[q] = 0.0;
+    if (ELLW > 0) {
+#pragma unroll
+      for (int q = 0; q < (ELLW + 1) / 2; ++q) u[ELLW + KD + q] = __hiloint2double((int)dummy_id, (int)dummy_id);
+    }
+  }
+  __device__ __forceinline__ double ell(int e) const { return u[e]; }
+  __device__ __forceinline__ double dense(int d) const { return u[ELLW + d]; }
+  __device__ __forceinline__ unsigned id(int e) const {
+    const double w = u[ELLW + KD + e / 2];
+    return (unsigned)((e & 1) ? __double2hiint(w) : __double2loint(w));
+  }
+  // both offsets become absolute shared-window addresses once per CTA (sbase < 64 KB - offsets, checked by the host)
+  __device__ __forceinline__ void rebase(unsigned sbase) {
+    if (ELLW > 0) {
+#pragma unroll
+      for (int q = 0; q < (ELLW + 1) / 2; ++q) {
+        const double w = u[ELLW + KD + q];
+        const unsigned add = sbase * 0x10001u;
+        u[ELLW + KD + q] = __hiloint2double((int)((unsigned)__double2hiint(w) + add), (int)((unsigned)__double2loint(w) + add));
+      }
+    }
+  }
+  // volatile: keeps the two extractions inside the iteration loop.  Hoisted, the 4*CPT addresses would be
+  // loop-invariant registers that ptxas then spills and reloads from local memory every iteration.
+  __device__ __forceinline__ unsigned yaddr(int e) const {
+    unsigned r; asm volatile("and.b32 %0, %1, 0xffff;" : "=r"(r) : "r"(id(e))); return r;
+  }
+  __device__ __forceinline__ unsigned paddr(int e) const {
+    unsigned r; asm volatile("shr.u32 %0, %1, 16;" : "=r"(r) : "r"(id(e))); return r;
+  }
+};
+
+// (kk+1)/(kk+2): Halpern weights, one constant-bank load instead of an fp64 division per iteration
+constexpr int kHalpTab = 2048;
+struct HalpTab {
+  double v[kHalpTab];
+  constexpr HalpTab() : v() {
+    for (int i = 0; i < kHalpTab; ++i) v[i] = (double)(i + 1) / (double)(i + 2);
+  }
+};
+__constant__ HalpTab c_halp = HalpTab();
+__device__ __forceinline__ double halpern_weight(int kk) {
+  return kk < kHalpTab ? c_halp.v[kk] : (double)(kk + 1) / (double)(kk + 2);
+}
+
+// volatile (not hoisted, not merged, ordered against the barriers) but no memory clobber: the compiler stays
+// free to schedule the thread-private C++ loads and stores around them
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v));
+}
+__device__ __forceinline__ double shx(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+// shared-memory map (bytes from the start of dynamic shared memory); the first two regions are fixed so that
+// the host can pack byte offsets into the column records
+constexpr int kYshBytes = 2048;            // ysh[256]   current dual iterate, published for the column pass
+constexpr int kProdBase = kYshBytes;       // prod[msS*RWP + 2] products S_ij * xbar_j (+ dummy slot)
+constexpr int kDL = 16;                    // lanes that add up one dense row / one norm
+enum { COLD_BEST_LB = 0, COLD_POBJ, COLD_DOBJ, COLD_OBJ_UPPER, COLD_KKT_BINV, COLD_W, COLD_R0SQ, COLD_RPREV, COLD_N = 8 };
+
+template <int NT, int CPT, int KD, int ELLW, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lpr_log2) {
+  constexpr int NW = NT / 32;
+  constexpr int NV = KD + 2;               // partial sums per thread: KD dense rows + 2 restart norms
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = dm.n, msS = dm.msS, m = dm.m, k = dm.k;
+  double* ysh = reinterpret_cast<double*>(smem_raw);
+  double* prod = reinterpret_cast<double*>(smem_raw + kProdBase);
+  const int prod_len = (msS * dm.RWP + 2 + 1) & ~1;
+  double* ytsh = prod + prod_len;        // [256] dual PDHG point (termination tests only)
+  double* ydsh = ytsh + 256;             // [8]   duals of the dense rows with the objective folded in
+  double* cold = ydsh + 8;               // [8]   per-node scalars used on norm / check iterations only
+  double* nrm = cold + COLD_N;           // [2]   the two restart norms of a norm iteration
+  double* redB = nrm + 2;                // NW * 8
+  double* redC = redB + NW * 8;          // NW * 8
+  int* s_node = reinterpret_cast<int*>(redC + NW * 8);       // [2]
+  double2* lu = reinterpret_cast<double2*>(redC + NW * 8 + 2);   // [CPT][NT] thread-private {l,u}
+  double* xts = reinterpret_cast<double*>(lu + NT * CPT);    // [CPT][NT] thread-private PDHG point xt
+  double* xas = xts + NT * CPT;                              // [CPT][NT] thread-private Halpern anchor
+  double* part = xas + NT * CPT;                             // [NV][NT]  per-thread partial sums of the dense rows / norms
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int LPR = 1 << lpr_log2;
+  // ---- roles in the row phase
+  const bool is_ell = tid < (msS << lpr_log2);               // LPR lanes per short structural row
+  const int vrow = (NT - 1 - tid) >> 4;                      // half-warps from the top: dense rows, then the 2 norms
+  const bool is_dense = vrow < NV;
+  const int sub = is_ell ? (tid & (LPR - 1)) : (tid & (kDL - 1));
+  const int row = is_ell ? (tid >> lpr_log2) : (is_dense && vrow < KD ? msS + vrow : -1);   // kernel row owned
+  const bool leader = row >= 0 && sub == 0;
+  const int dd = row - msS;                 // dense index of this thread's row (if >= 0)
+  const bool warp_has_dense = __any_sync(0xffffffffu, is_dense);
+  const bool warp_has_ell2 = LPR == 2 && __any_sync(0xffffffffu, is_ell);
+  const int trips = dm.reg_trips;           // 64-byte steps per lane over its share of a short row
+  const double2* prow = reinterpret_cast<const double2*>(prod + (is_ell ? (tid >> lpr_log2) * dm.RWP + 8 * sub : 0));
+  const double2* pden = reinterpret_cast<const double2*>(part + (is_dense ? vrow * NT + 2 * sub : 0));
+  const int norm_mask = p.norm_every - 1;   // norm_every is a power of two (host guarantees)
+  double2* lu_t = lu + tid;
+  double* xts_t = xts + tid;
+  double* xas_t = xas + tid;
+  double* part_t = part + tid;
+
+  // ---- the model, once per CTA
+  ColRec<ELLW, KD> rc[CPT];
+  {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned dummy = (unsigned)kProdBase + (unsigned)(msS * dm.RWP) * 8u;
+    if (sbase + dummy + 16u >= 65536u) __trap();             // 16-bit shared addresses (host keeps dummy < 60000)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * NT;
+      if (j < n) rc[c].load(dm.colrec2, j);
+      else rc[c].clear(dummy << 16);
+      rc[c].rebase(sbase);
+    }
+    for (int i = tid; i < prod_len; i += NT) prod[i] = 0.0;   // padding slots stay zero for ever
+  }
+
+  // S*v of this thread's row from the products / partial sums of the last column pass (after a barrier)
+  auto row_sum = [&](const bool with_norms) -> double {
+    double q = 0, q2 = 0;
+    if (is_ell) {
+      const double2* pp = prow;
+      for (int t = 0; t < trips; ++t) {
+        const double2 t0 = pp[0], t1 = pp[1], t2 = pp[2], t3 = pp[3];
+        q += t0.x; q2 += t0.y; q += t1.x; q2 += t1.y; q += t2.x; q2 += t2.y; q += t3.x; q2 += t3.y;
+        pp += 4 * LPR;
+      }
+    } else if (is_dense && (vrow < KD || with_norms)) {
+#pragma unroll
+      for (int t = 0; t < NT / 32; ++t) { const double2 t0 = pden[t * kDL]; q += t0.x; q2 += t0.y; }
+    }
+    q += q2;
+    if (warp_has_dense) {
+      double qd = is_dense ? q : 0.0;
+      qd += shx(qd, 8); qd += shx(qd, 4); qd += shx(qd, 2); qd += shx(qd, 1);
+      const double qe = LPR == 2 ? q + shx(q, 1) : q;        // (uniform condition: every lane shuffles)
+      q = is_dense ? qd : qe;
+    } else if (warp_has_ell2) q += shx(q, 1);
+    return q;
+  };
+
+  for (;;) {
+    if (tid == 0) s_node[0] = atomicAdd(b.work_counter, 1);
+    __syncthreads();
+    const int node = s_node[0];
+    if (node >= b.B) break;
+    if (b.skip && b.skip[node]) {
+      if (tid == 0) { b.status[node] = -1; b.iters[node] = 0; }
+      __syncthreads();
+      continue;
+    }
+    // ---------------------------------------------------------------- node load
+    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)node;   // row of the node's arrays
+    const int cost = b.cost_idx[(size_t)node * b.cost_stride];
+    const double* nrhs = b.rhs + (size_t)node * b.rhs_stride;
+    const double inv_dr_cost = 1.0 / dm.dr_k[msS + cost];
+    unsigned act = 0;                 // active dense rows (finite bound)
+    for (int o = 0; o < k; ++o)
+      if (fabs(nrhs[o]) < 1e19) act |= 1u << o;
+    for (int t = k; t < KD; ++t) act |= 1u << t;
+    double xb[CPT];
+    double a0[NV];
+#pragma unroll
+    for (int d = 0; d < NV; ++d) a0[d] = 0;
+    double cn2 = 0, cup = 0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * NT;
+      double lj = 0, uj = 0, xj = 0;
+      if (j < n) {
+        const double idc = 1.0 / dm.dc[j];
+        lj = (double)b.lb[srow * n + j] * idc;
+        uj = (double)b.ub[srow * n + j] * idc;
+        xj = b.warm_x ? b.warm_x[srow * n + j] * idc : 0.0;
+        xj = clampd(xj, lj, uj);
+      }
+      lu_t[c * NT] = make_double2(lj, uj);
+      xts_t[c * NT] = xj;
+      xas_t[c * NT] = xj;
+      xb[c] = xj;
+      double cj = 0;
+#pragma unroll
+      for (int d = 0; d < KD; ++d) { if (d == cost) cj = rc[c].dense(d); a0[d] = fma(rc[c].dense(d), xj, a0[d]); }
+      cj *= inv_dr_cost;
+      cn2 = fma(cj, cj, cn2);
+      cup += dmax(cj * lj, cj * uj);
+#pragma unroll
+      for (int e = 0; e < ELLW; ++e) sts_f64(rc[c].paddr(e), rc[c].ell(e) * xj);
+    }
+#pragma unroll
+    for (int d = 0; d < KD; ++d) part_t[d * NT] = a0[d];
+    double cs[2] = {cn2, cup};
+    bsum<2, NT>(cs, redB, tid);           // barrier: products and partial sums visible
+    // row state in registers (leaders); nlo/nhi are the negated row bounds (the dual step clamps to [-hi, -lo])
+    double r_nlo = HUGE_VAL, r_nhi = -HUGE_VAL, r_y = 0, r_ya = 0, r_sx = 0, r_sxa = 0, r_yt = 0, r_sxt = 0;
+    bool live = false;                    // leader of a row that can carry a nonzero dual
+    {
+      const double q = row_sum(false);    // S x0 of this thread's row
+      if (row >= 0) {
+        const double dri = dm.dr_k[row];
+        double lo, hi;
+        if (dd >= 0 && dd < k) { lo = -HUGE_VAL; hi = ((act >> dd) & 1u) ? dm.sgn * nrhs[dd] * dri : HUGE_VAL; }
+        else { lo = dm.lo_k[row]; hi = dm.hi_k[row]; }
+        double yi = b.warm_y ? b.warm_y[srow * m + row] / dri : 0.0;
+        if (lo == -HUGE_VAL) yi = dmin(yi, 0.0);
+        if (hi == HUGE_VAL) yi = dmax(yi, 0.0);
+        live = leader && (dd < 0 || ((act >> dd) & 1u));
+        if (!live) yi = 0.0;
+        r_nlo = -lo; r_nhi = -hi;
+        r_y = yi; r_ya = yi;
+        r_sx = q; r_sxa = q;
+        if (leader) {
+          if (dd < 0) ysh[row] = yi;
+          else ydsh[dd] = yi - (dd == cost ? inv_dr_cost : 0.0);
+        }
+      }
+    }
+    // primal weight w = |c| / |b| (scaled), unscaled |b| for the KKT denominator (uniform, m small)
+    double bn2 = 0, bn2_unscaled = dm.norm_row_bounds2;
+    for (int i = 0; i < m; ++i) {
+      const int di = i - msS;
+      double loi, hii;
+      if (di >= 0 && di < k) {
+        loi = -HUGE_VAL;
+        hii = ((act >> di) & 1u) ? dm.sgn * nrhs[di] * dm.dr_k[i] : HUGE_VAL;
+        if ((act >> di) & 1u) bn2_unscaled += nrhs[di] * nrhs[di];
+      } else { loi = dm.lo_k[i]; hii = dm.hi_k[i]; }
+      const double t = (hii != HUGE_VAL) ? hii : ((loi != -HUGE_VAL) ? loi : 0.0);
+      bn2 += t * t;
+    }
+    double tau, sigma, inv_sigma;
+    {
+      const double w = (cs[0] > 0 && bn2 > 0) ? sqrt(cs[0] / bn2) : 1.0;
+      tau = dm.eta / w; sigma = dm.eta * w; inv_sigma = 1.0 / sigma;
+      if (tid == 0) {
+        cold[COLD_W] = w; cold[COLD_R0SQ] = 0.0; cold[COLD_RPREV] = -1.0;
+        cold[COLD_BEST_LB] = -HUGE_VAL; cold[COLD_POBJ] = 0.0; cold[COLD_DOBJ] = -HUGE_VAL;
+        cold[COLD_OBJ_UPPER] = cs[1]; cold[COLD_KKT_BINV] = 1.0 / (1.0 + sqrt(bn2_unscaled));
+      }
+    }
+    __syncthreads();                       // ysh / ydsh visible; products consumed
+
+    int kk = 0, it = 0, status = MOIP_LP_ITERLIMIT;
+    double ah = 0.0;                       // Halpern weight of this iteration's column pass: x = ah*xbar + (1-ah)*xa
+    const int iter_cap = p.fixed_iters > 0 ? p.fixed_iters : p.max_iter;
+    int next_check = p.fixed_iters > 0 ? 0x7fffffff : p.check_every;
+
+    // ---------------------------------------------------------------- PDHG iterations
+    for (;;) {
+      ++it;
+      const bool norm_it = (kk & norm_mask) == 0;
+      const bool check_it = it == next_check;
+      const bool last_it = it >= iter_cap;
+      const double ah1 = 1.0 - ah;
+      // ---- column pass.  ydsh carries the objective (y_cost - 1/dr_cost), so  -(c - S^T y) = sum_i S_ij yd_i
+      {
+        double yd[KD];
+#pragma unroll
+        for (int d = 0; d < KD; ++d) yd[d] = ydsh[d];
+        double ye[CPT][ELLW > 0 ? ELLW : 1];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+          for (int e = 0; e < ELLW; ++e) ye[c][e] = lds_f64(rc[c].yaddr(e));
+        double aA[NV];
+#pragma unroll
+        for (int d = 0; d < NV; ++d) aA[d] = 0;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const double2 bx = lu_t[c * NT];
+          const double xaj = xas_t[c * NT];
+          double g = 0;
+#pragma unroll
+          for (int e = 0; e < ELLW; ++e) g = fma(rc[c].ell(e), ye[c][e], g);
+#pragma unroll
+          for (int d = 0; d < KD; ++d) g = fma(rc[c].dense(d), yd[d], g);
+          const double xj = fma(ah, xb[c], ah1 * xaj);
+          const double xtj = clampd(fma(tau, g, xj), bx.x, bx.y);
+          const double xbn = fma(2.0, xtj, -xj);
+          xb[c] = xbn; xts_t[c * NT] = xtj;
+          if (norm_it) {
+            const double d1 = xtj - xj, d2 = xtj - xaj;
+            aA[KD] = fma(d1, d1, aA[KD]);
+            aA[KD + 1] = fma(d2, d2, aA[KD + 1]);
+          }
+#pragma unroll
+          for (int d = 0; d < KD; ++d) aA[d] = fma(rc[c].dense(d), xbn, aA[d]);
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+          for (int e = 0; e < ELLW; ++e) sts_f64(rc[c].paddr(e), rc[c].ell(e) * xb[c]);
+#pragma unroll
+        for (int d = 0; d < KD; ++d) part_t[d * NT] = aA[d];
+        if (norm_it) { part_t[KD * NT] = aA[KD]; part_t[(KD + 1) * NT] = aA[KD + 1]; }
+      }
+      __syncthreads();                     // products and partial sums visible
+      // ---- row phase
+      double aB[3] = {0, 0, 0};
+      {
+        const double q = row_sum(norm_it);
+        if (is_dense && vrow >= KD && sub == 0 && norm_it) nrm[vrow - KD] = q;
+        r_sxt = 0.5 * (q + r_sx);
+        const double v = fma(r_y, inv_sigma, -q);
+        r_yt = live ? sigma * (v - clampd(v, r_nhi, r_nlo)) : 0.0;
+        if (norm_it && live) {
+          const double dy = r_yt - r_y, dya = r_yt - r_ya;
+          aB[0] = dy * dy; aB[1] = dy * (r_sxt - r_sx); aB[2] = dya * dya;
+        }
+      }
+      bool restart = false;
+      double fp2 = 0.0, w_new = 0.0;
+      const bool first_norm = kk == 0;
+      if (norm_it) {
+        bsum<3, NT>(aB, redB, tid);        // barrier: nrm visible
+        const double nx1 = nrm[0], nx2 = nrm[1];
+        const double wc = cold[COLD_W], r0sq = cold[COLD_R0SQ], rprev = cold[COLD_RPREV];
+        fp2 = dmax(0.0, fma(wc / dm.eta, nx1, fma(-2.0, aB[1], aB[0] * inv_sigma)));
+        if (kk != 0 && (fp2 <= 0.04 * r0sq || (fp2 <= 0.64 * r0sq && rprev >= 0.0 && fp2 > rprev) || 25 * kk >= 9 * it))
+          restart = true;
+        if (restart) {
+          const double dxn = sqrt(nx2), dyn = sqrt(aB[2]);
+          double w = wc;
+          if (dxn > 1e-10 && dyn > 1e-10) w = exp(0.5 * log(dyn / dxn) + 0.5 * log(w));
+          tau = dm.eta / w; sigma = dm.eta * w; inv_sigma = 1.0 / sigma;
+          w_new = w;
+        }
+      }
+      const bool need_stop_eval = check_it || last_it;
+      // ---- termination tests at (xt, yt); on the last iteration they also produce the outputs
+      bool stop = last_it;
+      if (need_stop_eval) {
+        if (leader) ytsh[row] = r_yt;
+        if (check_it) next_check += p.check_every;
+        __syncthreads();                   // ytsh visible
+        double aC[4] = {0, 0, 0, 0};       // pobj, dual (columns), dual (rows), primal residual^2 (unscaled)
+        double ytd[KD];
+#pragma unroll
+        for (int d = 0; d < KD; ++d) ytd[d] = ytsh[msS + d];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const double2 bx = lu_t[c * NT];
+          double g = 0, cj = 0;
+#pragma unroll
+          for (int e = 0; e < ELLW; ++e) g = fma(rc[c].ell(e), lds_f64(rc[c].yaddr(e) + (unsigned)((const char*)ytsh - (const char*)ysh)), g);
+#pragma unroll
+          for (int d = 0; d < KD; ++d) { g = fma(rc[c].dense(d), ytd[d], g); if (d == cost) cj = rc[c].dense(d); }
+          cj *= inv_dr_cost;
+          const double r = cj - g;
+          aC[0] = fma(cj, xts_t[c * NT], aC[0]);
+          aC[1] += (r > 0) ? r * bx.x : r * bx.y;
+        }
+        if (live) {
+          if (r_yt > 0) aC[2] = -r_yt * r_nlo;
+          else if (r_yt < 0) aC[2] = -r_yt * r_nhi;
+          const double viol = dmax(0.0, dmax(r_sxt + r_nhi, -r_nlo - r_sxt)) / dm.dr_k[row];
+          aC[3] = viol * viol;
+        }
+        bsum<4, NT>(aC, redC, tid);
+        const double pobj = aC[0], dobj = aC[1] + aC[2];
+        double best_lb = cold[COLD_BEST_LB];
+        const double obj_upper = cold[COLD_OBJ_UPPER], kkt_binv = cold[COLD_KKT_BINV];
+        if (p.fixed_iters > 0) best_lb = dobj;
+        else {
+          if (dobj > best_lb) best_lb = dobj;
+          const double gap = fabs(pobj - dobj);
+          const double rel = dmax(sqrt(aC[3]) * kkt_binv, gap / (1.0 + fabs(pobj) + fabs(dobj)));
+          const double cutoff = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
+          if (best_lb >= cutoff - p.cutoff_slack) { status = MOIP_LP_CUTOFF; stop = true; }
+          else if (best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
+          else if (rel <= p.eps) { status = MOIP_LP_CONVERGED; stop = true; }
+          else if (p.int_obj && sqrt(aC[3]) * kkt_binv <= 1e-5 && ceil(best_lb - 1e-6) >= ceil(pobj - 1e-3)) {
+            status = MOIP_LP_CONVERGED; stop = true;      // the integer-rounded bound cannot improve any further
+          }
+        }
+        __syncthreads();                   // every thread has read the cold scalars
+        if (tid == 0) { cold[COLD_BEST_LB] = best_lb; cold[COLD_POBJ] = pobj; cold[COLD_DOBJ] = dobj; }
+      }
+      if (stop) break;
+      // ---- restart or Halpern step of the row state; x follows in the next column pass
+      if (restart) {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) xas_t[c * NT] = xts_t[c * NT];
+        r_y = r_yt; r_ya = r_yt; r_sx = r_sxt; r_sxa = r_sxt;
+        kk = 0; ah = 0.0;
+      } else {
+        ah = halpern_weight(kk);           // (kk+1)/(kk+2)
+        const double c1 = 1.0 - ah;
+        r_y = fma(ah, 2.0 * r_yt - r_y, c1 * r_ya);
+        r_sx = fma(ah, 2.0 * r_sxt - r_sx, c1 * r_sxa);
+        ++kk;
+      }
+      if (leader) {
+        if (dd < 0) ysh[row] = r_y;
+        else ydsh[dd] = r_y - (dd == cost ? inv_dr_cost : 0.0);
+      }
+      __syncthreads();                     // duals visible; products consumed before the next column pass
+      if (norm_it && tid == 0) {           // deferred: every thread read the old values before the barrier
+        if (first_norm) cold[COLD_R0SQ] = fp2;
+        cold[COLD_RPREV] = restart ? -1.0 : fp2;
+        if (restart) cold[COLD_W] = w_new;
+      }
+    }
+    __syncthreads();                       // cold scalars of the last evaluation visible
+    const double pobj = cold[COLD_POBJ], best_lb = cold[COLD_BEST_LB], dobj_last = cold[COLD_DOBJ];
+
+    // ---------------------------------------------------------------- node store
+    // Reduced-cost tightening: with the Lagrangian bound L(yt) = dobj_last and reduced costs r, any
+    // point with x_j >= l_j + t has objective >= L + r_j t (r_j > 0), so columns can be tightened against
+    // the cutoff (strictly better integer solutions have objective <= cutoff - slack).  Valid for any yt.
+    if (b.rc_fix && b.cutoff && status != MOIP_LP_CUTOFF && status != MOIP_LP_INFEASIBLE) {
+      const double cutoff = *((volatile const double*)b.cutoff);
+      const double room = cutoff - p.cutoff_slack - dobj_last;
+      if (cutoff < HUGE_VAL && room >= 0.0 && dobj_last > -HUGE_VAL) {
+        double ytd[KD];
+#pragma unroll
+        for (int d = 0; d < KD; ++d) {
+          ytd[d] = ytsh[msS + d];
+          if (d == cost) ytd[d] -= inv_dr_cost;
+        }
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int j = tid + c * NT;
+          if (j < n) {
+            double g = 0;
+#pragma unroll
+            for (int e = 0; e < ELLW; ++e) g = fma(rc[c].ell(e), lds_f64(rc[c].yaddr(e) + (unsigned)((const char*)ytsh - (const char*)ysh)), g);
+#pragma unroll
+            for (int d = 0; d < KD; ++d) g = fma(rc[c].dense(d), ytd[d], g);
+            const double r = -g / dm.dc[j];        // unscaled reduced cost
+            int lbj = b.lb[srow * n + j], ubj = b.ub[srow * n + j];
+            if (lbj < ubj) {
+              if (r > 1e-9) {
+                const double t = floor(room / r + 1e-9);
+                if (t < (double)(ubj - lbj)) { ubj = lbj + (int)t; b.ub[srow * n + j] = ubj; }
+              } else if (r < -1e-9) {
+                const double t = floor(room / (-r) + 1e-9);
+                if (t < (double)(ubj - lbj)) { lbj = ubj - (int)t; b.lb[srow * n + j] = lbj; }
+              }
+            }
+          }
+        }
+      }
+    }
+    // unscaled PDHG point
+    double xo[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * NT;
+      xo[c] = (j < n) ? xts_t[c * NT] * dm.dc[j] : 0.0;
+      if (b.out_x && j < n) b.out_x[srow * n + j] = xo[c];
+    }
+    if (b.out_y && leader) b.out_y[srow * m + row] = r_yt * dm.dr_k[row];
+    if (b.branch_var) {           // the three most fractional columns, best first
+      int c0 = -1, c1 = -1;
+      for (int r = 0; r < 3; ++r) {
+        double bestf = -1.0, bestv = 0.0; int bestj = -1;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const int j = tid + c * NT;
+          const double f = fabs(xo[c] - rint(xo[c]));
+          if (j < n && j != c0 && j != c1 && f > bestf) { bestf = f; bestj = j; bestv = xo[c]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double of = __shfl_xor_sync(0xffffffffu, bestf, o);
+          const double ov = __shfl_xor_sync(0xffffffffu, bestv, o);
+          const int oj = __shfl_xor_sync(0xffffffffu, bestj, o);
+          if (of > bestf || (of == bestf && oj >= 0 && (bestj < 0 || oj < bestj))) { bestf = of; bestj = oj; bestv = ov; }
+        }
+        __syncthreads();
+        if (lane == 0) { redB[(tid >> 5) * 3] = bestf; redB[(tid >> 5) * 3 + 1] = (double)bestj; redB[(tid >> 5) * 3 + 2] = bestv; }
+        __syncthreads();
+        for (int wq = 0; wq < NW; ++wq) {     // every thread folds the warp results: uniform outcome
+          const double of = redB[wq * 3]; const int oj = (int)redB[wq * 3 + 1];
+          if (of > bestf || (of == bestf && oj >= 0 && (bestj < 0 || oj < bestj))) { bestf = of; bestj = oj; bestv = redB[wq * 3 + 2]; }
+        }
+        const int pick = (bestf > 1e-6) ? bestj : -1;
+        if (tid == 0) {
+          b.branch_var[(size_t)node * 3 + r] = pick;
+          if (b.branch_val) b.branch_val[(size_t)node * 3 + r] = (pick >= 0) ? bestv : 0.0;
+        }
+        if (r == 0) c0 = pick; else c1 = pick;
+      }
+    }
+    if (tid == 0) {
+      b.primal_obj[node] = pobj;
+      b.dual_bound[node] = best_lb;
+      b.status[node] = status;
+      b.iters[node] = it;
+    }
+    __syncthreads();
+  }
+}
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return v ? std::atoi(v) : dflt;
+}
+
+template <int NT, int CPT, int KD, int ELLW, int MINB>
+int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
+  auto kern = k1_reg_kernel<NT, CPT, KD, ELLW, MINB>;
+  const size_t prod_len = ((size_t)dm.msS * dm.RWP + 2 + 1) & ~(size_t)1;
+  const size_t smem = kYshBytes + sizeof(double) * (prod_len + 256 + 8 + COLD_N + 2 + (size_t)16 * (NT / 32) + 2 +
+                                                    (size_t)4 * NT * CPT + (size_t)(KD + 2) * NT);
+  static size_t configured = 0;
+  static int occ = 1;
+  if (smem > configured) {
+    MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    MOIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    if (occ < 1) { std::fprintf(stderr, "moip_b200: node LP does not fit on an SM (n=%d)\n", dm.n); return MOIP_ERR_LIMIT; }
+    const int cap = env_int("MOIP_K1_OCC", 0);
+    if (cap > 0 && cap < occ) occ = cap;
+    int pct = (int)(((smem + 1024) * occ * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    pct = env_int("MOIP_K1_CARVEOUT_PCT", pct);
+    MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    configured = smem;
+  }
+  long long grid = (long long)num_sms * occ;
+  if (grid > b.B) grid = b.B;
+  if (grid < 1) grid = 1;
+  int ne = 1;                              // restart-test cadence: largest power of two <= norm_every
+  while (ne * 2 <= p.norm_every) ne *= 2;
+  p.norm_every = ne;
+  kern<<<(unsigned)grid, NT, smem, st>>>(dm, b, p, dm.reg_lpr_log2);
+  MOIP_CUDA(cudaGetLastError());
+  return MOIP_OK;
+}
+
+// shape dispatch for one KD (one translation unit per KD keeps the build parallel)
+template <int KD>
+int launch_reg_kd(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
+  const bool wide = b.B <= env_int("MOIP_K1_WIDE_BELOW", 2 * num_sms);   // few nodes: spend threads on latency
+  if (dm.ell2_w == 2) {
+    if (dm.n <= 256) return launch_reg<128, 2, KD, 2, 4>(dm, b, p, num_sms, st);
+    if (dm.n <= 512) return launch_reg<256, 2, KD, 2, 3>(dm, b, p, num_sms, st);
+    if (wide) return launch_reg<512, 2, KD, 2, 1>(dm, b, p, num_sms, st);
+    return launch_reg<256, 4, KD, 2, 2>(dm, b, p, num_sms, st);
+  }
+  if (dm.ell2_w == 0) {
+    if (dm.n <= 256) return launch_reg<128, 2, KD, 0, 4>(dm, b, p, num_sms, st);
+    if (dm.n <= 512) return launch_reg<256, 2, KD, 0, 3>(dm, b, p, num_sms, st);
+    if (wide) return launch_reg<512, 2, KD, 0, 1>(dm, b, p, num_sms, st);
+    return launch_reg<256, 4, KD, 0, 2>(dm, b, p, num_sms, st);
+  }
+  return MOIP_ERR_UNSUPPORTED;
+}
+
+}  // namespace k1reg
+}  // namespace moip

@@ -554,6 +554,55 @@ int finalize_model(Model& M, std::string& err) {
       int32_t* ids = reinterpret_cast<int32_t*>(rec + E + M.KD);
       for (int e = 0; e < E; ++e) ids[e] = M.ellT2_row[(size_t)e * n + j];
     }
+    {
+      // register-resident kernel (k1_reg.cuh): LPR (1 or 2) lanes own a short row and add up the products the
+      // column pass scattered into prod[row*RWP + pos]; each lane reads 64 contiguous bytes per step (4 x 16 B)
+      // and steps by LPR*64 bytes.  The top 16*(KD+2) threads of the CTA add up the dense rows and the two
+      // restart norms instead.  RWP/2 odd puts the 8 lanes of a quarter-warp into 8 distinct 16-byte banks;
+      // positions inside a row are free, so they are dealt greedily such that the 16 columns a half-warp
+      // stores together hit distinct 8-byte banks too.  Offsets are bytes from the start of dynamic shared
+      // memory (ysh at 0, prod at 2048: k1reg::kProdBase).
+      const int nt_min = n <= 256 ? 128 : 256;
+      const int budget = nt_min - 16 * (M.KD + 2);            // threads left for the short rows
+      const int lg = (2 * M.msS <= budget) ? 1 : 0;
+      const int LPR = 1 << lg;
+      const int trips = std::max(1, (M.RW + 8 * LPR - 1) / (8 * LPR));
+      const int span = 8 * LPR * trips;                        // positions the row owners read
+      int rwp = span;
+      while (rwp % 4 != 2) ++rwp;
+      const unsigned prod_base = 2048;
+      M.RWP = M.RW > 0 ? rwp : 0;
+      M.reg_lpr_log2 = lg;
+      M.reg_trips = M.RW > 0 ? trips : 0;
+      M.reg_ok = M.fast_ok && M.KD >= 2 && M.KD <= 5 && (E == 0 || E == 2) && n > 64 && n <= 1024 && M.msS <= budget &&
+                 m <= 256 && prod_base + ((long long)M.msS * M.RWP + 2) * 8 < 60000;
+      M.colrec2 = M.colrec;
+      if (M.reg_ok && E > 0) {
+        std::vector<std::vector<char>> used(M.msS, std::vector<char>(std::max(1, span), 0));
+        const unsigned dummy = prod_base + (unsigned)(M.msS * M.RWP) * 8u;
+        for (int e = 0; e < E; ++e)
+          for (int g0 = 0; g0 < n; g0 += 16) {
+            unsigned banks = 0;
+            for (int j = g0; j < std::min(n, g0 + 16); ++j) {
+              double* rec = M.colrec2.data() + (size_t)j * M.col_units;
+              int32_t* ids = reinterpret_cast<int32_t*>(rec + E + M.KD);
+              const int r2 = M.ellT2_row[(size_t)e * n + j];
+              if (M.ellT2_val[(size_t)e * n + j] == 0.0) { ids[e] = (int32_t)(dummy << 16); continue; }   // padding entry
+              int pick = -1, fallback = -1;
+              for (int q = 0; q < span; ++q) {
+                if (used[r2][q]) continue;
+                if (fallback < 0) fallback = q;
+                if (!((banks >> ((r2 * M.RWP + q) & 15)) & 1u)) { pick = q; break; }
+              }
+              if (pick < 0) pick = fallback;
+              used[r2][pick] = 1;
+              banks |= 1u << ((r2 * M.RWP + pick) & 15);
+              const unsigned off = prod_base + (unsigned)(r2 * M.RWP + pick) * 8u;
+              ids[e] = (int32_t)((off << 16) | ((unsigned)r2 * 8u));
+            }
+          }
+      }
+    }
     M.rowrec.assign((size_t)std::max(1, M.RW) * std::max(1, M.msS) * 2, 0.0);
     for (int e = 0; e < M.RW; ++e)
       for (int r2 = 0; r2 < M.msS; ++r2) {

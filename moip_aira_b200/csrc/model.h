@@ -61,6 +61,12 @@ struct Model {
   int col_units = 0;                   // 8-byte units per column record (even)
   std::vector<double> colrec;          // [n][col_units]: ell2_w values | KD dense values | ell2_w row ids (int32 pairs)
   std::vector<double> rowrec;          // [RW][msS][2]: {value, column id (int32 in the low half)}
+  // register-resident kernel: products S_ij*xbar_j are scattered by the column pass into prod[row*RWP+pos]
+  bool reg_ok = false;
+  int RWP = 0;                         // padded short-row width (RWP/2 odd: bank-conflict-free 16-byte row reads)
+  int reg_lpr_log2 = 0;                // lanes per row owner group (log2)
+  int reg_trips = 0;                   // 64-byte steps per lane over its share of a short row
+  std::vector<double> colrec2;         // like colrec, ids packed as (product byte offset << 16 | dual byte offset)
   double eta = 0;                      // 0.99 / ||S||_2
   double norm_row_bounds2 = 0;         // sum of squares of finite scaled structural bounds
 };

@@ -94,6 +94,9 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   d.col_units = M.col_units;
   rc |= upload(c, M.colrec, &d.colrec);
   rc |= upload(c, M.rowrec, &d.rowrec);
+  d.reg_ok = M.reg_ok ? 1 : 0; d.RWP = M.RWP; d.reg_lpr_log2 = M.reg_lpr_log2; d.reg_trips = M.reg_trips;
+  if (std::getenv("MOIP_K1_NOREG")) d.reg_ok = 0;
+  rc |= upload(c, M.colrec2, &d.colrec2);
   rc |= upload(c, M.dr_k, &d.dr_k);
   rc |= upload(c, M.lo_k, &d.lo_k);
   rc |= upload(c, M.hi_k, &d.hi_k);
@@ -207,7 +210,7 @@ extern "C" int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params) {
   p.cutoff_slack = 0.0; p.int_obj = 0;
   c->stats.kernel_launches += 1;
   c->stats.node_lps += b.B;
-  return d.fast_ok ? launch_k1_fast(d, b, p, c->num_sms, c->stream) : launch_k1(d, b, p, c->num_sms, c->stream);
+  return launch_k1_any(d, b, p, c->num_sms, c->stream);
 }
 
 extern "C" int moip_lp_batch_download(moip_ctx* c, double* primal_obj, double* dual_bound, int* status, int* iters,
@@ -532,7 +535,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     b.branch_var = r_branch.p; b.branch_val = r_bval.p; b.skip = r_flag.p;
     b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = r_cutoff.p; b.work_counter = r_counter.p;
     b.cost_idx = r_ids.p + Bmax;   // one shared cost index, staged behind the ids (cost_stride = 0)
-    if (dm.fast_ok ? launch_k1_fast(dm, b, lp, num_sms, stream) : launch_k1(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
+    if (launch_k1_any(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
     if (launch_k4_round(dm, B, r_ids.p, pool.wx, pool.lb, pool.ub, r_xr.p, r_cobj.p, r_cfeas.p, stream)) return MOIP_ERR_CUDA;
     stats.kernel_launches += 3;
     unsigned char* H = h_round.p;

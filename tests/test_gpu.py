@@ -150,13 +150,23 @@ def test_k4_verify_exact(mb, examples, stem):
 # ----------------------------------------------------------------------------------------- K1
 def _lp_case(kind):
     from oracle.lpformat import synthetic_ap, synthetic_kp
-    return synthetic_ap(8, 3, 1) if kind == "ap8" else synthetic_ap(30, 3, 1) if kind == "ap30" else synthetic_kp(40, 4, 1)
+    kind = kind.split("-")[0]
+    k = 4 if kind.startswith("kp") else 3
+    if kind[-1] in "24" and kind[-2] == "k":        # e.g. ap16k4: 4 objectives
+        k = int(kind[-1]); kind = kind[:-2]
+    size = int(kind[2:])
+    return synthetic_ap(size, k, 1) if kind.startswith("ap") else synthetic_kp(size, k, 1)
 
 
-@pytest.mark.parametrize("kind,B", [("ap8", 24), ("kp40", 48), ("ap30", 16)])
-def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B):
+# K1 has three code paths: k1_fast (n <= 64), the register-resident k1_reg with NT x CPT = 128x2 (n <= 256),
+# 256x2 (n <= 512), 256x4 (throughput) and 512x2 (few nodes), and the generic kernel.  "-thr" pins 256x4.
+@pytest.mark.parametrize("kind,B", [("ap8", 24), ("kp40", 48), ("ap30", 16), ("ap30-thr", 16), ("ap12", 24), ("ap20", 16),
+                                    ("kp100", 32), ("ap16k4", 16), ("ap12k2", 16)])
+def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B, monkeypatch):
     """LP relaxation objectives within 1e-6 relative of HiGHS (stand-in: the reference pins no LP value)
     and of the C restatement; infeasible nodes are recognised; the dual bound is a valid bound."""
+    if kind.endswith("-thr"):
+        monkeypatch.setenv("MOIP_K1_WIDE_BELOW", "0")
     from oracle import pdhg_oracle as po
     from oracle.lpformat import write_lp
     model = _lp_case(kind)
@@ -186,12 +196,15 @@ def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B):
     ctx.close()
 
 
-def test_k1_fixed_iterations_match_port(mb, tmp_path):
+@pytest.mark.parametrize("kind", ["ap8", "ap12", "ap30", "ap30-thr", "kp100"])
+def test_k1_fixed_iterations_match_port(mb, tmp_path, kind, monkeypatch):
     """Same arithmetic as the C restatement: after a fixed number of iterations the iterates agree."""
     from oracle import pdhg_oracle as po
     from oracle.lpformat import write_lp
-    model = _lp_case("ap8")
-    path = str(tmp_path / "ap8.lp")
+    if kind.endswith("-thr"):
+        monkeypatch.setenv("MOIP_K1_WIDE_BELOW", "0")
+    model = _lp_case(kind)
+    path = str(tmp_path / f"{kind}.lp")
     write_lp(model, path)
     ctx = mb.Context(mb.Problem(path))
     cost, rhs, masks = po.sample_node_batch(model, 12, seed=3)
