@@ -254,7 +254,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k1_pdhg_kernel",
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "k1_reg_kernel<256,4,3,2,2>",
                          "algorithmic_bytes_per_node_iter": bytes_iter,
                          "node_iters_per_launch": my_iters / args.steps,
                          "note": "iterates stay in shared memory across iterations; HBM traffic is far below the "

@@ -129,7 +129,16 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" :: "r"(addr), "d"(v));
 }
+template <int OFF>
+__device__ __forceinline__ void lds_f64x2(unsigned addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a), "=d"(b) : "r"(addr), "n"(OFF));
+}
 __device__ __forceinline__ double shx(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+struct TrueT { static constexpr bool value = true; };
+struct FalseT { static constexpr bool value = false; };
+// role word of a thread in the row phase (kept opaque so that it is not re-derived from tid every iteration)
+enum : unsigned { ROLE_ELL = 1u, ROLE_DENSE = 2u, ROLE_NORM = 4u, ROLE_LEADER = 8u, ROLE_WARP_DENSE = 16u, ROLE_WARP_ELL2 = 32u,
+                  ROLE_LIVE = 64u };
 
 // shared-memory map (bytes from the start of dynamic shared memory); the first two regions are fixed so that
 // the host can pack byte offsets into the column records
@@ -161,19 +170,27 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
   double* part = xas + NT * CPT;                             // [NV][NT]  per-thread partial sums of the dense rows / norms
   const int tid = threadIdx.x, lane = tid & 31;
   const int LPR = 1 << lpr_log2;
-  // ---- roles in the row phase
-  const bool is_ell = tid < (msS << lpr_log2);               // LPR lanes per short structural row
-  const int vrow = (NT - 1 - tid) >> 4;                      // half-warps from the top: dense rows, then the 2 norms
-  const bool is_dense = vrow < NV;
-  const int sub = is_ell ? (tid & (LPR - 1)) : (tid & (kDL - 1));
-  const int row = is_ell ? (tid >> lpr_log2) : (is_dense && vrow < KD ? msS + vrow : -1);   // kernel row owned
-  const bool leader = row >= 0 && sub == 0;
+  // ---- roles in the row phase: LPR lanes per short structural row from thread 0 up, one half-warp per dense
+  // row and per restart norm from the top thread down
+  int row;                                  // kernel row owned by this thread's group, -1 = none
+  unsigned role, psum;                      // flags; shared address of the first 16 bytes this thread adds up
+  {
+    const bool is_ell = tid < (msS << lpr_log2);
+    const int vrow = (NT - 1 - tid) >> 4;
+    const bool is_dense = vrow < NV;
+    const int sub = is_ell ? (tid & (LPR - 1)) : (tid & (kDL - 1));
+    row = is_ell ? (tid >> lpr_log2) : (is_dense && vrow < KD ? msS + vrow : -1);
+    role = (is_ell ? ROLE_ELL : 0u) | (is_dense ? ROLE_DENSE : 0u) | (is_dense && vrow >= KD ? ROLE_NORM : 0u) |
+           (row >= 0 && sub == 0 ? ROLE_LEADER : 0u);
+    if (is_dense && vrow >= KD && sub == 0) row = KD - 2 - vrow;           // leader of a norm group: -2 / -3 = slot 0 / 1 of nrm[]
+    if (__any_sync(0xffffffffu, is_dense)) role |= ROLE_WARP_DENSE;
+    if (LPR == 2 && __any_sync(0xffffffffu, is_ell)) role |= ROLE_WARP_ELL2;
+    const double* src = is_ell ? prod + (tid >> lpr_log2) * dm.RWP + 8 * sub : (is_dense ? part + vrow * NT + 2 * sub : prod);
+    psum = (unsigned)__cvta_generic_to_shared(src);
+    asm volatile("" : "+r"(role), "+r"(psum), "+r"(row));
+  }
   const int dd = row - msS;                 // dense index of this thread's row (if >= 0)
-  const bool warp_has_dense = __any_sync(0xffffffffu, is_dense);
-  const bool warp_has_ell2 = LPR == 2 && __any_sync(0xffffffffu, is_ell);
   const int trips = dm.reg_trips;           // 64-byte steps per lane over its share of a short row
-  const double2* prow = reinterpret_cast<const double2*>(prod + (is_ell ? (tid >> lpr_log2) * dm.RWP + 8 * sub : 0));
-  const double2* pden = reinterpret_cast<const double2*>(part + (is_dense ? vrow * NT + 2 * sub : 0));
   const int norm_mask = p.norm_every - 1;   // norm_every is a power of two (host guarantees)
   double2* lu_t = lu + tid;
   double* xts_t = xts + tid;
@@ -199,24 +216,37 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
   // S*v of this thread's row from the products / partial sums of the last column pass (after a barrier)
   auto row_sum = [&](const bool with_norms) -> double {
     double q = 0, q2 = 0;
-    if (is_ell) {
-      const double2* pp = prow;
+    if (role & ROLE_ELL) {
+      unsigned a = psum;
       for (int t = 0; t < trips; ++t) {
-        const double2 t0 = pp[0], t1 = pp[1], t2 = pp[2], t3 = pp[3];
-        q += t0.x; q2 += t0.y; q += t1.x; q2 += t1.y; q += t2.x; q2 += t2.y; q += t3.x; q2 += t3.y;
-        pp += 4 * LPR;
+        double x0, y0, x1, y1, x2, y2, x3, y3;
+        lds_f64x2<0>(a, x0, y0); lds_f64x2<16>(a, x1, y1); lds_f64x2<32>(a, x2, y2); lds_f64x2<48>(a, x3, y3);
+        q += x0; q2 += y0; q += x1; q2 += y1; q += x2; q2 += y2; q += x3; q2 += y3;
+        a += 64u << lpr_log2;
       }
-    } else if (is_dense && (vrow < KD || with_norms)) {
+    } else if ((role & ROLE_DENSE) && (with_norms || !(role & ROLE_NORM))) {
+      double x[NT / 32], y[NT / 32];
 #pragma unroll
-      for (int t = 0; t < NT / 32; ++t) { const double2 t0 = pden[t * kDL]; q += t0.x; q2 += t0.y; }
+      for (int t = 0; t < NT / 32; ++t) {
+        if (t == 0) lds_f64x2<0>(psum, x[t], y[t]); else if (t == 1) lds_f64x2<256>(psum, x[t], y[t]);
+        else if (t == 2) lds_f64x2<512>(psum, x[t], y[t]); else if (t == 3) lds_f64x2<768>(psum, x[t], y[t]);
+        else if (t == 4) lds_f64x2<1024>(psum, x[t], y[t]); else if (t == 5) lds_f64x2<1280>(psum, x[t], y[t]);
+        else if (t == 6) lds_f64x2<1536>(psum, x[t], y[t]); else if (t == 7) lds_f64x2<1792>(psum, x[t], y[t]);
+        else if (t == 8) lds_f64x2<2048>(psum, x[t], y[t]); else if (t == 9) lds_f64x2<2304>(psum, x[t], y[t]);
+        else if (t == 10) lds_f64x2<2560>(psum, x[t], y[t]); else if (t == 11) lds_f64x2<2816>(psum, x[t], y[t]);
+        else if (t == 12) lds_f64x2<3072>(psum, x[t], y[t]); else if (t == 13) lds_f64x2<3328>(psum, x[t], y[t]);
+        else if (t == 14) lds_f64x2<3584>(psum, x[t], y[t]); else lds_f64x2<3840>(psum, x[t], y[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < NT / 32; ++t) { q += x[t]; q2 += y[t]; }
     }
     q += q2;
-    if (warp_has_dense) {
-      double qd = is_dense ? q : 0.0;
+    if (role & ROLE_WARP_DENSE) {
+      double qd = (role & ROLE_DENSE) ? q : 0.0;
       qd += shx(qd, 8); qd += shx(qd, 4); qd += shx(qd, 2); qd += shx(qd, 1);
       const double qe = LPR == 2 ? q + shx(q, 1) : q;        // (uniform condition: every lane shuffles)
-      q = is_dense ? qd : qe;
-    } else if (warp_has_ell2) q += shx(q, 1);
+      q = (role & ROLE_DENSE) ? qd : qe;
+    } else if (role & ROLE_WARP_ELL2) q += shx(q, 1);
     return q;
   };
 
@@ -274,7 +304,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
     bsum<2, NT>(cs, redB, tid);           // barrier: products and partial sums visible
     // row state in registers (leaders); nlo/nhi are the negated row bounds (the dual step clamps to [-hi, -lo])
     double r_nlo = HUGE_VAL, r_nhi = -HUGE_VAL, r_y = 0, r_ya = 0, r_sx = 0, r_sxa = 0, r_yt = 0, r_sxt = 0;
-    bool live = false;                    // leader of a row that can carry a nonzero dual
+    role &= ~ROLE_LIVE;                   // LIVE: leader of a row that can carry a nonzero dual
     {
       const double q = row_sum(false);    // S x0 of this thread's row
       if (row >= 0) {
@@ -285,16 +315,17 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
         double yi = b.warm_y ? b.warm_y[srow * m + row] / dri : 0.0;
         if (lo == -HUGE_VAL) yi = dmin(yi, 0.0);
         if (hi == HUGE_VAL) yi = dmax(yi, 0.0);
-        live = leader && (dd < 0 || ((act >> dd) & 1u));
-        if (!live) yi = 0.0;
+        const bool live = (role & ROLE_LEADER) && (dd < 0 || ((act >> dd) & 1u));
+        if (live) role |= ROLE_LIVE; else yi = 0.0;
         r_nlo = -lo; r_nhi = -hi;
         r_y = yi; r_ya = yi;
         r_sx = q; r_sxa = q;
-        if (leader) {
+        if (role & ROLE_LEADER) {
           if (dd < 0) ysh[row] = yi;
           else ydsh[dd] = yi - (dd == cost ? inv_dr_cost : 0.0);
         }
       }
+      asm volatile("" : "+r"(role));
     }
     // primal weight w = |c| / |b| (scaled), unscaled |b| for the KKT denominator (uniform, m small)
     double bn2 = 0, bn2_unscaled = dm.norm_row_bounds2;
@@ -326,65 +357,72 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
     const int iter_cap = p.fixed_iters > 0 ? p.fixed_iters : p.max_iter;
     int next_check = p.fixed_iters > 0 ? 0x7fffffff : p.check_every;
 
+    // ---- column pass.  ydsh carries the objective (y_cost - 1/dr_cost), so  -(c - S^T y) = sum_i S_ij yd_i.
+    // NORM: also accumulate the two restart norms; xt is only written out when somebody will read it
+    // (restart / termination tests happen on norm, check and last iterations).
+    auto column_pass = [&](auto norm_tag, const double ah, const double tau, const bool keep_xt) {
+      constexpr bool NORM = decltype(norm_tag)::value;
+      const double ah1 = 1.0 - ah;
+      double yd[KD];
+#pragma unroll
+      for (int d = 0; d < KD; ++d) yd[d] = ydsh[d];
+      double ye[CPT][ELLW > 0 ? ELLW : 1];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int e = 0; e < ELLW; ++e) ye[c][e] = lds_f64(rc[c].yaddr(e));
+      double aA[NV];
+#pragma unroll
+      for (int d = 0; d < NV; ++d) aA[d] = 0;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const double2 bx = lu_t[c * NT];
+        const double xaj = xas_t[c * NT];
+        double g = 0, gd = 0;
+#pragma unroll
+        for (int e = 0; e < ELLW; ++e) g = fma(rc[c].ell(e), ye[c][e], g);
+#pragma unroll
+        for (int d = 0; d < KD; ++d) gd = fma(rc[c].dense(d), yd[d], gd);
+        g += gd;
+        const double xj = fma(ah, xb[c], ah1 * xaj);
+        const double xtj = clampd(fma(tau, g, xj), bx.x, bx.y);
+        const double xbn = fma(2.0, xtj, -xj);
+        xb[c] = xbn;
+        if (NORM || keep_xt) xts_t[c * NT] = xtj;
+        if (NORM) {
+          const double d1 = xtj - xj, d2 = xtj - xaj;
+          aA[KD] = fma(d1, d1, aA[KD]);
+          aA[KD + 1] = fma(d2, d2, aA[KD + 1]);
+        }
+#pragma unroll
+        for (int d = 0; d < KD; ++d) aA[d] = fma(rc[c].dense(d), xbn, aA[d]);
+      }
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int e = 0; e < ELLW; ++e) sts_f64(rc[c].paddr(e), rc[c].ell(e) * xb[c]);
+#pragma unroll
+      for (int d = 0; d < (NORM ? NV : KD); ++d) part_t[d * NT] = aA[d];
+    };
+
     // ---------------------------------------------------------------- PDHG iterations
     for (;;) {
       ++it;
       const bool norm_it = (kk & norm_mask) == 0;
       const bool check_it = it == next_check;
       const bool last_it = it >= iter_cap;
-      const double ah1 = 1.0 - ah;
-      // ---- column pass.  ydsh carries the objective (y_cost - 1/dr_cost), so  -(c - S^T y) = sum_i S_ij yd_i
-      {
-        double yd[KD];
-#pragma unroll
-        for (int d = 0; d < KD; ++d) yd[d] = ydsh[d];
-        double ye[CPT][ELLW > 0 ? ELLW : 1];
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-#pragma unroll
-          for (int e = 0; e < ELLW; ++e) ye[c][e] = lds_f64(rc[c].yaddr(e));
-        double aA[NV];
-#pragma unroll
-        for (int d = 0; d < NV; ++d) aA[d] = 0;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-          const double2 bx = lu_t[c * NT];
-          const double xaj = xas_t[c * NT];
-          double g = 0;
-#pragma unroll
-          for (int e = 0; e < ELLW; ++e) g = fma(rc[c].ell(e), ye[c][e], g);
-#pragma unroll
-          for (int d = 0; d < KD; ++d) g = fma(rc[c].dense(d), yd[d], g);
-          const double xj = fma(ah, xb[c], ah1 * xaj);
-          const double xtj = clampd(fma(tau, g, xj), bx.x, bx.y);
-          const double xbn = fma(2.0, xtj, -xj);
-          xb[c] = xbn; xts_t[c * NT] = xtj;
-          if (norm_it) {
-            const double d1 = xtj - xj, d2 = xtj - xaj;
-            aA[KD] = fma(d1, d1, aA[KD]);
-            aA[KD + 1] = fma(d2, d2, aA[KD + 1]);
-          }
-#pragma unroll
-          for (int d = 0; d < KD; ++d) aA[d] = fma(rc[c].dense(d), xbn, aA[d]);
-        }
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-#pragma unroll
-          for (int e = 0; e < ELLW; ++e) sts_f64(rc[c].paddr(e), rc[c].ell(e) * xb[c]);
-#pragma unroll
-        for (int d = 0; d < KD; ++d) part_t[d * NT] = aA[d];
-        if (norm_it) { part_t[KD * NT] = aA[KD]; part_t[(KD + 1) * NT] = aA[KD + 1]; }
-      }
+      if (norm_it) column_pass(TrueT{}, ah, tau, true);
+      else column_pass(FalseT{}, ah, tau, check_it || last_it);
       __syncthreads();                     // products and partial sums visible
       // ---- row phase
       double aB[3] = {0, 0, 0};
       {
         const double q = row_sum(norm_it);
-        if (is_dense && vrow >= KD && sub == 0 && norm_it) nrm[vrow - KD] = q;
+        if (norm_it && row < -1) nrm[-2 - row] = q;
         r_sxt = 0.5 * (q + r_sx);
         const double v = fma(r_y, inv_sigma, -q);
-        r_yt = live ? sigma * (v - clampd(v, r_nhi, r_nlo)) : 0.0;
-        if (norm_it && live) {
+        r_yt = (role & ROLE_LIVE) ? sigma * (v - clampd(v, r_nhi, r_nlo)) : 0.0;
+        if (norm_it && (role & ROLE_LIVE)) {
           const double dy = r_yt - r_y, dya = r_yt - r_ya;
           aB[0] = dy * dy; aB[1] = dy * (r_sxt - r_sx); aB[2] = dya * dya;
         }
@@ -411,7 +449,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
       // ---- termination tests at (xt, yt); on the last iteration they also produce the outputs
       bool stop = last_it;
       if (need_stop_eval) {
-        if (leader) ytsh[row] = r_yt;
+        if (role & ROLE_LEADER) ytsh[row] = r_yt;
         if (check_it) next_check += p.check_every;
         __syncthreads();                   // ytsh visible
         double aC[4] = {0, 0, 0, 0};       // pobj, dual (columns), dual (rows), primal residual^2 (unscaled)
@@ -431,7 +469,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
           aC[0] = fma(cj, xts_t[c * NT], aC[0]);
           aC[1] += (r > 0) ? r * bx.x : r * bx.y;
         }
-        if (live) {
+        if (role & ROLE_LIVE) {
           if (r_yt > 0) aC[2] = -r_yt * r_nlo;
           else if (r_yt < 0) aC[2] = -r_yt * r_nhi;
           const double viol = dmax(0.0, dmax(r_sxt + r_nhi, -r_nlo - r_sxt)) / dm.dr_k[row];
@@ -471,7 +509,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
         r_sx = fma(ah, 2.0 * r_sxt - r_sx, c1 * r_sxa);
         ++kk;
       }
-      if (leader) {
+      if (role & ROLE_LEADER) {
         if (dd < 0) ysh[row] = r_y;
         else ydsh[dd] = r_y - (dd == cost ? inv_dr_cost : 0.0);
       }
@@ -531,7 +569,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
       xo[c] = (j < n) ? xts_t[c * NT] * dm.dc[j] : 0.0;
       if (b.out_x && j < n) b.out_x[srow * n + j] = xo[c];
     }
-    if (b.out_y && leader) b.out_y[srow * m + row] = r_yt * dm.dr_k[row];
+    if (b.out_y && (role & ROLE_LEADER)) b.out_y[srow * m + row] = r_yt * dm.dr_k[row];
     if (b.branch_var) {           // the three most fractional columns, best first
       int c0 = -1, c1 = -1;
       for (int r = 0; r < 3; ++r) {
@@ -614,17 +652,16 @@ int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cu
 // shape dispatch for one KD (one translation unit per KD keeps the build parallel)
 template <int KD>
 int launch_reg_kd(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
-  const bool wide = b.B <= env_int("MOIP_K1_WIDE_BELOW", 2 * num_sms);   // few nodes: spend threads on latency
+  // fewer, fatter threads win: with more warps per node the barriers and the partial-sum phase cost more than
+  // the shorter column pass saves (measured on B200, 3AP30: 512x2 and 320x3 are 15-25 % slower than 256x4)
   if (dm.ell2_w == 2) {
     if (dm.n <= 256) return launch_reg<128, 2, KD, 2, 4>(dm, b, p, num_sms, st);
-    if (dm.n <= 512) return launch_reg<256, 2, KD, 2, 3>(dm, b, p, num_sms, st);
-    if (wide) return launch_reg<512, 2, KD, 2, 1>(dm, b, p, num_sms, st);
+    if (dm.n <= 512) return launch_reg<256, 2, KD, 2, 2>(dm, b, p, num_sms, st);
     return launch_reg<256, 4, KD, 2, 2>(dm, b, p, num_sms, st);
   }
   if (dm.ell2_w == 0) {
     if (dm.n <= 256) return launch_reg<128, 2, KD, 0, 4>(dm, b, p, num_sms, st);
-    if (dm.n <= 512) return launch_reg<256, 2, KD, 0, 3>(dm, b, p, num_sms, st);
-    if (wide) return launch_reg<512, 2, KD, 0, 1>(dm, b, p, num_sms, st);
+    if (dm.n <= 512) return launch_reg<256, 2, KD, 0, 2>(dm, b, p, num_sms, st);
     return launch_reg<256, 4, KD, 0, 2>(dm, b, p, num_sms, st);
   }
   return MOIP_ERR_UNSUPPORTED;

@@ -113,7 +113,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->bb_max_iter = env_int("MOIP_BB_MAX_ITER", 3000);
   c->bb_eps = env_double("MOIP_BB_EPS", 1e-5);
   c->bb_check = env_int("MOIP_BB_CHECK", 32);
-  c->norm_every = env_int("MOIP_NORM_EVERY", 4);
+  c->norm_every = env_int("MOIP_NORM_EVERY", 16);
   c->bb_levels = env_int("MOIP_BB_LEVELS", 3);
   *out = c;
   return MOIP_OK;

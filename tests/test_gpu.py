@@ -159,14 +159,12 @@ def _lp_case(kind):
 
 
 # K1 has three code paths: k1_fast (n <= 64), the register-resident k1_reg with NT x CPT = 128x2 (n <= 256),
-# 256x2 (n <= 512), 256x4 (throughput) and 512x2 (few nodes), and the generic kernel.  "-thr" pins 256x4.
-@pytest.mark.parametrize("kind,B", [("ap8", 24), ("kp40", 48), ("ap30", 16), ("ap30-thr", 16), ("ap12", 24), ("ap20", 16),
+# 256x2 (n <= 512) and 256x4 (n <= 1024), and the generic kernel.
+@pytest.mark.parametrize("kind,B", [("ap8", 24), ("kp40", 48), ("ap30", 16), ("ap12", 24), ("ap20", 16),
                                     ("kp100", 32), ("ap16k4", 16), ("ap12k2", 16)])
 def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B, monkeypatch):
     """LP relaxation objectives within 1e-6 relative of HiGHS (stand-in: the reference pins no LP value)
     and of the C restatement; infeasible nodes are recognised; the dual bound is a valid bound."""
-    if kind.endswith("-thr"):
-        monkeypatch.setenv("MOIP_K1_WIDE_BELOW", "0")
     from oracle import pdhg_oracle as po
     from oracle.lpformat import write_lp
     model = _lp_case(kind)
@@ -196,21 +194,19 @@ def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("kind", ["ap8", "ap12", "ap30", "ap30-thr", "kp100"])
+@pytest.mark.parametrize("kind", ["ap8", "ap12", "ap30", "kp100"])
 def test_k1_fixed_iterations_match_port(mb, tmp_path, kind, monkeypatch):
     """Same arithmetic as the C restatement: after a fixed number of iterations the iterates agree."""
     from oracle import pdhg_oracle as po
     from oracle.lpformat import write_lp
-    if kind.endswith("-thr"):
-        monkeypatch.setenv("MOIP_K1_WIDE_BELOW", "0")
     model = _lp_case(kind)
     path = str(tmp_path / f"{kind}.lp")
     write_lp(model, path)
     ctx = mb.Context(mb.Problem(path))
     cost, rhs, masks = po.sample_node_batch(model, 12, seed=3)
-    for iters in (1, 7, 40):
+    for iters in (1, 7, 40, 100):
         got = ctx.lp_batch_solve(cost, rhs, masks, mb.Context.lp_params(fixed_iters=iters), want_x=True)
-        port = po.pdhg_ref(model, cost, rhs, masks, fixed_iters=iters, norm_every=int(os.environ.get("MOIP_NORM_EVERY", "4")))
+        port = po.pdhg_ref(model, cost, rhs, masks, fixed_iters=iters, norm_every=int(os.environ.get("MOIP_NORM_EVERY", "16")))
         assert np.all(got["iters"] == iters)
         assert np.allclose(got["x"], port["x"], rtol=0, atol=1e-9)
         assert np.allclose(got["primal_obj"], port["primal_obj"], rtol=1e-10, atol=1e-9)

@@ -12,10 +12,11 @@ d = tempfile.mkdtemp(); p = os.path.join(d, name + ".lp")
 ctx = mb.Context(mb.Problem(p))
 cost, rhs, masks = instances.sample_node_batch(ctx, B)
 ctx.lp_batch_upload(cost, rhs, masks)
-params = ctx.lp_params(fixed_iters=iters) if iters > 0 else ctx.lp_params(eps=1e-6)
+params = ctx.lp_params(fixed_iters=iters) if iters > 0 else ctx.lp_params(eps=1e-6, check_every=int(os.environ.get("MOIP_CHECK_EVERY", "32")))
 for _ in range(2):
     ctx.lp_batch_run(params); r = ctx.lp_batch_download()
 torch.cuda.synchronize(); t = time.perf_counter()
 ctx.lp_batch_run(params); r = ctx.lp_batch_download()
 dt = time.perf_counter() - t
-print(f"{name} B={B} iters={iters}: {dt*1e3:.2f} ms, {r['iters'].sum()/dt:.3g} node-iter/s")
+print(f"{name} B={B} iters={iters}: {dt*1e3:.2f} ms, {r['iters'].sum()/dt:.3g} node-iter/s, {B/dt:.0f} LP/s, mean iters {r['iters'].mean():.0f}, "
+      f"status counts {np.bincount(r['status'], minlength=4).tolist()}")
