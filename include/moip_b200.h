@@ -173,6 +173,23 @@ int moip_split_strips(int sense, int biggest, int smallest, int num_threads, int
 int moip_pareto_front(moip_ctx* c, int split, int num_threads, int split_normal, int* rows_out,
                       int cap, int* n_rows);
 
+/* ---- worker pool: the reference's one-thread-per-strip model (src/aira.cpp:1920-1933, one CPLEX
+ * environment per thread) with one solver context per host thread on ONE device, so that the B&B rounds
+ * of concurrent strips share the GPU.  Every worker keeps its own caches. */
+typedef struct moip_pool moip_pool;
+int moip_pool_create(moip_model* m, int device, int workers, moip_pool** out);
+void moip_pool_destroy(moip_pool* p);
+int moip_pool_workers(const moip_pool* p);
+int moip_pool_stats(const moip_pool* p, moip_stats* out);                   /* summed over the workers */
+int moip_pool_get_limit(moip_pool* p, int obj, int sense, const double* rhs, int* result, int* mip_status);
+/* split_optimise (src/aira.cpp:1886-1943) for nstrips explicit (start, stop) pairs, dealt dynamically to
+ * the workers; rows_out receives the feasible result vectors (k ints per row, unsorted) */
+int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const double* start_stop, int* rows_out, int cap,
+                         int* n_rows);
+/* main() with --split -t num_threads (src/aira.cpp:269-276, :1945-1990): every level's strips run
+ * concurrently on the pool; rows_out = sorted, de-duplicated front */
+int moip_pool_pareto_front(moip_pool* p, int num_threads, int split_normal, int* rows_out, int cap, int* n_rows);
+
 const char* moip_version(void);
 
 #ifdef __cplusplus

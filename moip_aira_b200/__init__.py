@@ -94,6 +94,13 @@ _SIGS = {
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "moip_split_strips": (_i, [_i, _i, _i, _i, _i, _pd]),
     "moip_pareto_front": (_i, [_vp, _i, _i, _i, _pi, _i, _pi]),
+    "moip_pool_create": (_i, [_vp, _i, _i, C.POINTER(_vp)]),
+    "moip_pool_destroy": (None, [_vp]),
+    "moip_pool_workers": (_i, [_vp]),
+    "moip_pool_stats": (_i, [_vp, C.POINTER(Stats)]),
+    "moip_pool_get_limit": (_i, [_vp, _i, _i, _pd, _pi, _pi]),
+    "moip_pool_run_strips": (_i, [_vp, _i, _i, _pd, _pi, _i, _pi]),
+    "moip_pool_pareto_front": (_i, [_vp, _i, _i, _pi, _i, _pi]),
     "moip_version": (C.c_char_p, []),
 }
 EXPORTED = sorted(_SIGS)
@@ -285,6 +292,67 @@ class Context:
     def close(self):
         if self._h:
             _lib.moip_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WorkerPool:
+    """One solver context per host thread on one GPU (the reference's thread-per-strip model,
+    src/aira.cpp:1920-1933): the EPP strips of a level run concurrently and share the device."""
+
+    def __init__(self, problem: Problem, device: int = 0, workers: int = 8):
+        self.problem = problem
+        h = _vp()
+        _check(_lib.moip_pool_create(problem._h, device, int(workers), C.byref(h)), "pool_create")
+        self._h = h
+
+    @property
+    def workers(self):
+        return _lib.moip_pool_workers(self._h)
+
+    def get_limit(self, obj, rhs, sense=None):
+        k = self.problem.objcnt
+        r = np.ascontiguousarray(rhs, dtype=np.float64)
+        res = np.zeros(k, dtype=np.int32)
+        st = C.c_int(0)
+        _check(_lib.moip_pool_get_limit(self._h, int(obj), self.problem.objsen if sense is None else int(sense), _dp(r), _ip(res),
+                                        C.byref(st)), "pool_get_limit")
+        return st.value, ([int(v) for v in res] if st.value != MIP_INFEASIBLE else None)
+
+    def run_strips(self, n_obj, strips, cap=1 << 14):
+        """strips: list of (start, stop); returns the feasible result rows found (unsorted)."""
+        k = self.problem.objcnt
+        ss = np.ascontiguousarray(np.asarray(strips, dtype=np.float64).reshape(-1, 2))
+        rows = np.zeros((cap, k), dtype=np.int32)
+        n = C.c_int(0)
+        _check(_lib.moip_pool_run_strips(self._h, int(n_obj), len(ss), _dp(ss), _ip(rows), cap, C.byref(n)), "pool_run_strips")
+        if n.value > cap:
+            return self.run_strips(n_obj, strips, cap=n.value)
+        return [tuple(int(v) for v in r) for r in rows[:n.value]]
+
+    def pareto_front(self, num_threads=8, split_normal=False, cap=1 << 16):
+        k = self.problem.objcnt
+        rows = np.zeros((cap, k), dtype=np.int32)
+        n = C.c_int(0)
+        _check(_lib.moip_pool_pareto_front(self._h, int(num_threads), int(split_normal), _ip(rows), cap, C.byref(n)),
+               "pool_pareto_front")
+        if n.value > cap:
+            return self.pareto_front(num_threads, split_normal, cap=n.value)
+        return [tuple(int(v) for v in r) for r in rows[:n.value]]
+
+    def stats(self):
+        s = Stats()
+        _check(_lib.moip_pool_stats(self._h, C.byref(s)), "pool_stats")
+        return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+    def close(self):
+        if self._h:
+            _lib.moip_pool_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <mutex>
 
 #include "../../include/moip_b200.h"
 
@@ -93,6 +94,9 @@ struct LpParams {
   double cutoff_slack;        // stop when bound >= cutoff - slack (integer objectives: 1 - 1e-6)
   int int_obj;                // objective is integer valued: stop once ceil(bound) cannot rise any more
 };
+
+// serialises the one-time cudaFuncSetAttribute blocks of the launchers (worker threads share the kernels)
+std::mutex& launch_cfg_mutex();
 
 int launch_k1_any(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);   // best path the model allows
 int launch_k1_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);

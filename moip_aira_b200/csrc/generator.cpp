@@ -6,14 +6,18 @@
 //
 // State per worker: rhs[k] (current bounds), hi_seen[]/lo_seen[] (the reference's max[]/min[]
 // trackers), misses (its infcnt), last_missed (inflast), level (depth_level), walking (onwalk).
+#include <atomic>
 #include <climits>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 #include "solver.h"
 
-int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which);
+int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which,
+                moip::CacheRecord* rec_out);
 
 namespace moip {
 
@@ -128,12 +132,11 @@ struct GpuBackend : GenBackend {
   }
   int find(const double* rhs, int* hit, int* infeasible, int* result) override {
     int idx = -1, which = -1;
-    if (infeasibles->host.empty() && sols->host.empty()) { *hit = 0; return MOIP_OK; }
-    int rc = cache_find2(c, infeasibles, sols, 1, rhs, sense, &idx, &which);
+    CacheRecord r{};
+    int rc = cache_find2(c, infeasibles, sols, 1, rhs, sense, &idx, &which, &r);
     if (rc) return rc;
     *hit = idx >= 0;
     if (idx >= 0) {
-      const CacheRecord& r = (which == 0 ? infeasibles : sols)->host[idx];
       *infeasible = r.infeasible;
       for (int j = 0; j < c->dm.k; ++j) result[j] = r.result[j];
     }
@@ -275,6 +278,187 @@ int epp_level(moip_ctx* c, int n_obj, int num_threads, int split_normal, std::ve
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------ worker pool
+// The reference runs one std::thread per strip / worker, each with its own CPLEX environment
+// (src/aira.cpp:297-308, :1920-1933).  Here the same host threads each own a solver context (stream,
+// node pool, staging buffers, caches) on ONE device: a single B&B round keeps only a fraction of the 148 SMs
+// busy, concurrent workers fill the rest.  Strips are dealt dynamically; every worker keeps its own
+// `here` / `infeasibles` stores (the reference shares them under a mutex, which only changes IP counts).
+struct moip_pool {
+  moip_model* model = nullptr;
+  int device = 0;
+  std::vector<moip_ctx*> ctx;
+  std::vector<cudaStream_t> streams;
+};
+
+extern "C" int moip_pool_create(moip_model* m, int device, int workers, moip_pool** out) {
+  if (!m || !out || workers < 1 || workers > 64) return MOIP_ERR_ARG;
+  moip_pool* p = new moip_pool();
+  p->model = m; p->device = device;
+  for (int w = 0; w < workers; ++w) {
+    cudaStream_t st = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+      std::fprintf(stderr, "moip_b200: cannot create a stream on device %d (this library has no CPU fallback)\n", device);
+      moip_pool_destroy(p);
+      return MOIP_ERR_CUDA;
+    }
+    p->streams.push_back(st);
+    moip_ctx* c = nullptr;
+    int rc = moip_ctx_create(m, device, st, &c);
+    if (rc) { moip_pool_destroy(p); return rc; }
+    p->ctx.push_back(c);
+  }
+  *out = p;
+  return MOIP_OK;
+}
+
+extern "C" void moip_pool_destroy(moip_pool* p) {
+  if (!p) return;
+  for (moip_ctx* c : p->ctx) moip_ctx_destroy(c);
+  cudaSetDevice(p->device);
+  for (cudaStream_t st : p->streams) cudaStreamDestroy(st);
+  delete p;
+}
+
+extern "C" int moip_pool_workers(const moip_pool* p) { return p ? (int)p->ctx.size() : -1; }
+
+extern "C" int moip_pool_stats(const moip_pool* p, moip_stats* out) {
+  if (!p || !out) return MOIP_ERR_ARG;
+  *out = moip_stats{};
+  for (moip_ctx* c : p->ctx) {
+    out->ip_solved += c->stats.ip_solved; out->bb_nodes += c->stats.bb_nodes; out->node_lps += c->stats.node_lps;
+    out->lp_iterations += c->stats.lp_iterations; out->kernel_launches += c->stats.kernel_launches;
+    out->cache_queries += c->stats.cache_queries; out->solver_seconds += c->stats.solver_seconds;
+  }
+  return MOIP_OK;
+}
+
+extern "C" int moip_pool_get_limit(moip_pool* p, int obj, int sense, const double* rhs, int* result, int* mip_status) {
+  if (!p || p->ctx.empty()) return MOIP_ERR_ARG;
+  return moip_get_limit(p->ctx[0], obj, sense, rhs, result, mip_status);
+}
+
+// split_optimise (src/aira.cpp:1886-1943) for an explicit list of strips: start_stop holds nstrips (start, stop)
+// pairs; rows_out receives the feasible result vectors found (k ints per row, unsorted, duplicates possible)
+extern "C" int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const double* start_stop, int* rows_out, int cap,
+                                    int* n_rows) {
+  if (!p || p->ctx.empty() || nstrips < 0 || (nstrips > 0 && !start_stop) || !n_rows) return MOIP_ERR_ARG;
+  const int k = p->ctx[0]->dm.k;
+  if (n_obj < 1 || n_obj > k) return MOIP_ERR_ARG;
+  const int W = std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
+  std::atomic<int> next(0), failed(0);
+  // `here` and `infeasibles` are shared by the strips of a level, like the reference's threads share them
+  // (src/aira.cpp:1918-1933); MOIP_POOL_PRIVATE_CACHES=1 gives every worker its own pair instead
+  const bool shared = !std::getenv("MOIP_POOL_PRIVATE_CACHES");
+  moip_cache *sh_here = nullptr, *sh_inf = nullptr;
+  if (shared) {
+    int rc0 = moip_cache_create(p->ctx[0], &sh_here);
+    if (!rc0) rc0 = moip_cache_create(p->ctx[0], &sh_inf);
+    if (rc0) { moip_cache_destroy(sh_here); moip_cache_destroy(sh_inf); return rc0; }
+  }
+  std::vector<std::vector<int>> found(W);
+  auto work = [&](int wi) {
+    moip_ctx* c = p->ctx[wi];
+    moip_cache *here = sh_here, *infeasibles = sh_inf;
+    int rc = MOIP_OK;
+    if (!shared) {
+      rc = moip_cache_create(c, &here);
+      if (!rc) rc = moip_cache_create(c, &infeasibles);
+    }
+    while (!rc && !failed.load()) {
+      const int t = next.fetch_add(1);
+      if (t >= nstrips) break;
+      moip_worker w{};
+      w.id = t; w.n_obj = n_obj; w.split = 1;
+      for (int i = 0; i < k; ++i) w.perm[i] = i;                            // thread.cpp:124-133
+      w.split_start = start_stop[2 * t]; w.split_stop = start_stop[2 * t + 1];
+      rc = moip_optimise(c, &w, here, infeasibles);
+    }
+    if (!rc && here && !shared)
+      for (auto& r : here->host) if (!r.infeasible) found[wi].insert(found[wi].end(), r.result, r.result + k);   // :1934-1942
+    if (rc) failed.store(rc);
+    if (!shared) { moip_cache_destroy(here); moip_cache_destroy(infeasibles); }
+  };
+  std::vector<std::thread> th;
+  for (int wi = 1; wi < W; ++wi) th.emplace_back(work, wi);
+  work(0);
+  for (auto& t : th) t.join();
+  if (shared) {
+    if (!failed.load())
+      for (auto& r : sh_here->host) if (!r.infeasible) found[0].insert(found[0].end(), r.result, r.result + k);
+    moip_cache_destroy(sh_here);
+    moip_cache_destroy(sh_inf);
+  }
+  if (failed.load()) return failed.load();
+  int n = 0;
+  for (auto& f : found)
+    for (size_t i = 0; i + k <= f.size(); i += k, ++n)
+      if (rows_out && n < cap) for (int j = 0; j < k; ++j) rows_out[(size_t)n * k + j] = f[i + j];
+  *n_rows = n;
+  return MOIP_OK;
+}
+
+namespace {
+
+// split_setup (src/aira.cpp:1945-1990) on a pool: the strips of one level run concurrently
+int epp_level_pool(moip_pool* p, int n_obj, int num_threads, int split_normal, std::vector<std::vector<int>>& sols) {
+  moip_ctx* c = p->ctx[0];
+  const int k = c->dm.k, sense = c->model->M.sense;
+  const bool is_min = sense == MOIP_SENSE_MIN;
+  std::vector<double> free_rhs(k, is_min ? kInf : -kInf);
+  std::vector<int> res(k, 0);
+  int st = 0, rc;
+  if (n_obj == 1) {
+    if ((rc = c->get_limit(0, sense, free_rhs.data(), res.data(), &st))) return rc;
+    if (st != MOIP_MIP_INFEASIBLE) sols.push_back(res);
+    return MOIP_OK;
+  }
+  std::vector<std::vector<int>> lower;
+  if ((rc = epp_level_pool(p, n_obj - 1, num_threads, split_normal, lower))) return rc;
+  if (lower.empty()) return MOIP_OK;
+  if ((rc = c->get_limit(n_obj - 1, sense, free_rhs.data(), res.data(), &st))) return rc;
+  if (st == MOIP_MIP_INFEASIBLE) return MOIP_OK;
+  int biggest, smallest;
+  if (is_min) {
+    smallest = res[n_obj - 1]; biggest = INT_MIN;
+    for (auto& s : lower) biggest = std::max(biggest, s[n_obj - 1]);
+    if (biggest == smallest) biggest = INT_MAX;
+  } else {
+    biggest = res[n_obj - 1]; smallest = INT_MAX;
+    for (auto& s : lower) smallest = std::min(smallest, s[n_obj - 1]);
+    if (biggest == smallest) smallest = INT_MIN;
+  }
+  std::vector<double> ss(2 * (size_t)num_threads);
+  if ((rc = moip_split_strips(sense, biggest, smallest, num_threads, split_normal, ss.data()))) return rc;
+  int cap = 1 << 14, nrows = 0;
+  std::vector<int> rows((size_t)cap * k);
+  for (;;) {
+    if ((rc = moip_pool_run_strips(p, n_obj, num_threads, ss.data(), rows.data(), cap, &nrows))) return rc;
+    if (nrows <= cap) break;
+    cap = nrows; rows.assign((size_t)cap * k, 0);       // (re-solves; only for fronts beyond 16k rows)
+  }
+  for (int i = 0; i < nrows; ++i) sols.emplace_back(rows.begin() + (size_t)i * k, rows.begin() + (size_t)(i + 1) * k);
+  return MOIP_OK;
+}
+
+}  // namespace
+
+extern "C" int moip_pool_pareto_front(moip_pool* p, int num_threads, int split_normal, int* rows_out, int cap, int* n_rows) {
+  if (!p || p->ctx.empty() || !n_rows) return MOIP_ERR_ARG;
+  const int k = p->ctx[0]->dm.k;
+  if (num_threads < 1) num_threads = 1;
+  std::vector<std::vector<int>> sols;
+  int rc = epp_level_pool(p, k, num_threads, split_normal, sols);
+  if (rc) return rc;
+  moip_cache* all = nullptr;
+  if ((rc = moip_cache_create(p->ctx[0], &all))) return rc;
+  std::vector<double> zero(k, 0.0);
+  for (auto& s : sols) moip_cache_insert(all, zero.data(), s.data(), 0);
+  *n_rows = moip_cache_sort_unique(all, rows_out, cap);
+  moip_cache_destroy(all);
+  return MOIP_OK;
+}
 
 extern "C" int moip_pareto_front(moip_ctx* c, int split, int num_threads, int split_normal, int* rows_out, int cap,
                                  int* n_rows) {

@@ -447,6 +447,7 @@ int launch_fast(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, c
   const size_t smem = sizeof(double) * ((size_t)CS * dm.n + (size_t)2 * dm.m + (size_t)24 * (NT / 32));
   static size_t configured = 0;
   static int occ = 1;
+  std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
   if (smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // leave the rest of the 256 KB array to L1: the packed model image (tens of KB) is re-read by every
@@ -462,7 +463,9 @@ int launch_fast(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, c
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     configured = smem;
   }
-  long long grid = (long long)num_sms * occ;
+  const int occ_now = occ;
+  cfg_lock.unlock();
+  long long grid = (long long)num_sms * occ_now;
   if (grid > b.B) grid = b.B;
   if (grid < 1) grid = 1;
   int lpr_log2 = 0;

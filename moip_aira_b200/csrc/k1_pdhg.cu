@@ -370,10 +370,12 @@ template <int NT>
 int launch_nt(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   const size_t smem = sizeof(double) * ((size_t)5 * dm.n + (size_t)8 * dm.m + (size_t)24 * (NT / 32));
   static size_t configured = 0;
+  std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
   if (smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(k1_pdhg_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  cfg_lock.unlock();
   int occ = 1;
   MOIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_pdhg_kernel<NT>, NT, smem));
   if (occ < 1) { std::fprintf(stderr, "moip_b200: node LP does not fit in shared memory (n=%d)\n", dm.n); return MOIP_ERR_LIMIT; }

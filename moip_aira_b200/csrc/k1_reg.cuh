@@ -625,6 +625,7 @@ int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cu
                                                     (size_t)4 * NT * CPT + (size_t)(KD + 2) * NT);
   static size_t configured = 0;
   static int occ = 1;
+  std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
   if (smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -638,7 +639,9 @@ int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cu
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     configured = smem;
   }
-  long long grid = (long long)num_sms * occ;
+  const int occ_now = occ;
+  cfg_lock.unlock();
+  long long grid = (long long)num_sms * occ_now;
   if (grid > b.B) grid = b.B;
   if (grid < 1) grid = 1;
   int ne = 1;                              // restart-test cadence: largest power of two <= norm_every

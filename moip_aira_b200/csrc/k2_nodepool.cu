@@ -208,10 +208,12 @@ int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const i
   if (B <= 0) return MOIP_OK;
   const size_t smem = sizeof(int) * 4 * (size_t)dm.n;
   static size_t configured = 0;
+  std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
   if (smem > 48 * 1024 && smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(k2_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  cfg_lock.unlock();
   int grid = B < 148 * 8 ? B : 148 * 8;
   k2_propagate_kernel<<<grid, kPropThreads, smem, st>>>(dm, pool, B, ids, obj_lo, obj_hi, max_rounds, flag, leaf_obj);
   MOIP_CUDA(cudaGetLastError());

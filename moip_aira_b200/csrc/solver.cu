@@ -12,6 +12,11 @@
 
 using namespace moip;
 
+std::mutex& moip::launch_cfg_mutex() {
+  static std::mutex m;
+  return m;
+}
+
 namespace {
 
 template <class T>
@@ -246,14 +251,15 @@ extern "C" int moip_lp_batch_solve(moip_ctx* c, int B, const int* cost_idx, cons
 }
 
 // ------------------------------------------------------------------------------------ K3 cache
-int moip_cache::sync_to_device() {
+int moip_cache::sync_to_device(cudaStream_t st) {
   if (synced == host.size()) return MOIP_OK;
-  MOIP_CUDA(cudaSetDevice(ctx->device));
-  if (dev.ensure(host.size(), true, ctx->stream)) return MOIP_ERR_CUDA;
+  MOIP_CUDA(cudaSetDevice(device));
+  if (dev.ensure(host.size(), true, st)) return MOIP_ERR_CUDA;
   MOIP_CUDA(cudaMemcpyAsync(dev.p + synced, host.data() + synced, sizeof(CacheRecord) * (host.size() - synced),
-                            cudaMemcpyHostToDevice, ctx->stream));
-  // host.data() may be reallocated by a later insert: finish the copy before returning
-  MOIP_CUDA(cudaStreamSynchronize(ctx->stream));
+                            cudaMemcpyHostToDevice, st));
+  // host.data() may be reallocated by a later insert: finish the copy before returning.  `st` is the calling
+  // worker's own stream (a store shared by a pool must not wait for another worker's B&B round).
+  MOIP_CUDA(cudaStreamSynchronize(st));
   synced = host.size();
   return MOIP_OK;
 }
@@ -281,17 +287,27 @@ extern "C" int moip_cache_insert(moip_cache* s, const double* ip, const int* res
   CacheRecord r{};
   for (int i = 0; i < s->k; ++i) { r.ip[i] = ip[i]; r.result[i] = (infeasible || !result) ? 0 : result[i]; }
   r.infeasible = infeasible ? 1 : 0;
+  std::lock_guard<std::mutex> lk(s->mu);
   s->host.push_back(r);
   return MOIP_OK;
 }
-extern "C" int moip_cache_size(const moip_cache* s) { return s ? (int)s->host.size() : -1; }
+extern "C" int moip_cache_size(const moip_cache* s) {
+  if (!s) return -1;
+  std::lock_guard<std::mutex> lk(const_cast<moip_cache*>(s)->mu);
+  return (int)s->host.size();
+}
 
 // shared by the public batch call and the generator (two stores, one launch, one sync)
-int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which) {
+int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which,
+                CacheRecord* rec_out) {
   MOIP_CUDA(cudaSetDevice(c->device));
   const int k = c->dm.k;
-  if (s0 && s0->sync_to_device()) return MOIP_ERR_CUDA;
-  if (s1 && s1->sync_to_device()) return MOIP_ERR_CUDA;
+  // both stores stay locked from the device sync to the read-back: another worker's insert may move the host array
+  std::unique_lock<std::mutex> l0, l1;
+  if (s0) l0 = std::unique_lock<std::mutex>(s0->mu);
+  if (s1 && s1 != s0) l1 = std::unique_lock<std::mutex>(s1->mu);
+  if (s0 && s0->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
+  if (s1 && s1->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
   if (c->q_ip.ensure((size_t)Q * k) || c->q_out.ensure(Q) || c->q_which.ensure(Q) || c->h_q.ensure((size_t)2 * Q)) return MOIP_ERR_CUDA;
   MOIP_CUDA(cudaMemcpyAsync(c->q_ip.p, ip, sizeof(double) * Q * k, cudaMemcpyHostToDevice, c->stream));
   DevCache e{}; e.k = k; e.size = 0; e.rec = nullptr;
@@ -304,16 +320,21 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
   MOIP_CUDA(cudaStreamSynchronize(c->stream));
   std::memcpy(first_match, c->h_q.p, sizeof(int) * Q);
   if (which) std::memcpy(which, c->h_q.p + Q, sizeof(int) * Q);
+  if (rec_out)
+    for (int q = 0; q < Q; ++q)
+      if (first_match[q] >= 0) rec_out[q] = ((c->h_q.p[Q + q] == 0 ? s0 : s1))->host[first_match[q]];
   return MOIP_OK;
 }
 
 extern "C" int moip_cache_find_batch(moip_cache* s, int Q, const double* ip, int sense, int* first_match) {
   if (!s || Q < 0 || (Q > 0 && (!ip || !first_match))) return MOIP_ERR_ARG;
   if (Q == 0) return MOIP_OK;
-  return cache_find2(s->ctx, s, nullptr, Q, ip, sense, first_match, nullptr);
+  return cache_find2(s->ctx, s, nullptr, Q, ip, sense, first_match, nullptr, nullptr);
 }
 extern "C" int moip_cache_get(const moip_cache* s, int i, double* ip, int* result, int* infeasible) {
-  if (!s || i < 0 || i >= (int)s->host.size()) return MOIP_ERR_ARG;
+  if (!s) return MOIP_ERR_ARG;
+  std::lock_guard<std::mutex> lk(const_cast<moip_cache*>(s)->mu);
+  if (i < 0 || i >= (int)s->host.size()) return MOIP_ERR_ARG;
   const CacheRecord& r = s->host[i];
   for (int j = 0; j < s->k; ++j) { if (ip) ip[j] = r.ip[j]; if (result) result[j] = r.result[j]; }
   if (infeasible) *infeasible = r.infeasible;
@@ -321,6 +342,7 @@ extern "C" int moip_cache_get(const moip_cache* s, int i, double* ip, int* resul
 }
 extern "C" int moip_cache_merge(moip_cache* s, moip_cache* other) {
   if (!s || !other || s == other || s->k != other->k) return MOIP_ERR_ARG;
+  std::scoped_lock lk(s->mu, other->mu);
   std::vector<CacheRecord> merged;
   merged.reserve(s->host.size() + other->host.size());
   merged.insert(merged.end(), other->host.begin(), other->host.end());   // splice at begin()
@@ -333,6 +355,7 @@ extern "C" int moip_cache_merge(moip_cache* s, moip_cache* other) {
 }
 extern "C" int moip_cache_sort_unique(moip_cache* s, int* rows, int cap) {
   if (!s) return -1;
+  std::lock_guard<std::mutex> lk(s->mu);
   const int k = s->k;
   // Result::operator< : infeasible first, then descending lexicographic (reference src/result.cpp:9-29)
   std::stable_sort(s->host.begin(), s->host.end(), [k](const CacheRecord& a, const CacheRecord& b) {

@@ -1,6 +1,7 @@
 // Host driver state behind the opaque handles of include/moip_b200.h.
 #pragma once
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -67,7 +68,8 @@ struct moip_cache {
   std::vector<moip::CacheRecord> host;   // insertion order
   moip::DBuf<moip::CacheRecord> dev;
   size_t synced = 0;                     // records [0, synced) are on the device
-  int sync_to_device();
+  std::mutex mu;                         // the stores are shared by the worker threads of a pool (src/solutions.h:41-44)
+  int sync_to_device(cudaStream_t st);
   moip::DevCache view() const;
 };
 

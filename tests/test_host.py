@@ -36,6 +36,8 @@ def test_no_gpu_means_loud_failure(lib, examples):
     pr = lib.Problem(examples["2AP05"]["path"])
     with pytest.raises(lib.MoipError):
         lib.Context(pr)
+    with pytest.raises(lib.MoipError):
+        lib.WorkerPool(pr, 0, 2)
 
 
 @pytest.mark.parametrize("stem", SMALL + ["2KP50", "moip_2_30_1_knapsack"])
