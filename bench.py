@@ -134,6 +134,9 @@ def main():
     ap.add_argument("--workload", default="ap30", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-fronts", action="store_true")
+    ap.add_argument("--front-instance", default="ap3_15_1", help="synthetic instance of tests/golden/synthetic.json whose "
+                    "Pareto front is timed with the EPP strips sharded over the ranks (ap3_12_1, ap3_15_1, ap3_20_1, kp4_25_1 ...)")
+    ap.add_argument("--front-strips-per-gpu", type=int, default=12)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,6 +227,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
     max_ms = float(t.item())
+    # ---- the unambiguous-work figure of SURVEY.md 8d-6: every LP runs exactly 1000 iterations
+    fixed = ctx.lp_params(fixed_iters=1000)
+    ctx.lp_batch_run(fixed); ctx.lp_batch_download()
+    fe = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    flush.fill_(1)
+    fe[0].record(stream); ctx.lp_batch_run(fixed); fe[1].record(stream)
+    ctx.lp_batch_download()
+    fixed_ms = fe[0].elapsed_time(fe[1])
     # ---- end-to-end path through the host-buffer call (pinned host memory)
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     hc, hr, hm = pin(cost), pin(rhs), pin(masks)
@@ -241,8 +252,6 @@ def main():
     clocks = sampler.stop()
     status = np.bincount(r["status"], minlength=4)
 
-    if rank != 0:
-        return 0
     n, m, k = pr.n, pr.m, pr.objcnt
     bytes_iter = algorithmic_bytes_per_node_iter(n, m, k)
     peak, peak_kind = measured_peak()
@@ -250,7 +259,7 @@ def main():
     my_iters = iters_total
     achieved = my_iters * bytes_iter / (dev_ms * 1e-3) / 1e9
     value = world * B * args.steps / (max_ms * 1e-3)
-    line = {"metric": "node_lp_relaxations_per_sec", "value": value, "unit": "LP/s", "n_gpus": world,
+    line = {} if rank != 0 else {"metric": "node_lp_relaxations_per_sec", "value": value, "unit": "LP/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -263,7 +272,12 @@ def main():
                     "h2d_bytes_per_step": int(hc.nbytes + hr.nbytes + hm.nbytes), "d2h_bytes_per_step": int(B * (8 + 8 + 4 + 4))},
             "gpu_launches": int(launches), "clocks": clocks,
             "lp": {"mean_iters": my_iters / (args.steps * B), "status_counts": status.tolist(),
-                   "node_iters_per_sec": float(it.item()) / (max_ms * 1e-3)}}
+                   "node_iters_per_sec": float(it.item()) / (max_ms * 1e-3),
+                   "fixed_1000_iterations": {"ms": fixed_ms, "node_iters_per_sec": B * 1000 / (fixed_ms * 1e-3),
+                                             "roofline_frac": B * 1000 * bytes_iter / (fixed_ms * 1e-3) / 1e9 / peak}}}
+    tr = os.path.join(ROOT, "profiles", "k1_traffic.json")      # dram bytes per launch of this command from ncu --set full
+    if rank == 0 and os.path.exists(tr):
+        line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
     if world == 1:
         sample = max(cores, min(args.cpu_sample, B))
@@ -273,8 +287,69 @@ def main():
                                           f"one process per core; stand-in, NOT CPLEX) and the C port of K1 ({p:.1f} LP/s)"}
         if not args.no_fronts:
             line["time_to_front_s"] = time_to_front(mb, local, stream.cuda_stream)
-    print(json.dumps(line))
+            line["cpu_baseline"]["front"] = cpu_front("ap3_10_1", mb, local, stream.cuda_stream, tmp)
+    print_line = rank == 0
+    if not args.no_fronts:
+        ctx.close()
+        fr = synthetic_front(args.front_instance, args.front_strips_per_gpu * world, local, tmp)   # collective: every rank
+        if print_line:
+            line.setdefault("time_to_front_s", {})[f"{args.front_instance} --split -t {args.front_strips_per_gpu * world}"] = fr
+    if print_line:
+        print(json.dumps(line))
     return 0
+
+
+def cpu_front(name, mb, device, stream, tmp):
+    """Time-to-front side by side on one small synthetic instance: the CPU restatement of the reference's
+    generator driven by HiGHS (stand-in for aira + CPLEX, which cannot be installed; one core, -t 1) against
+    this library's default run on the GPU."""
+    from moip_aira_b200 import instances
+    from oracle import aira_oracle as ao            # checker / baseline only
+    from oracle.lpformat import read_model
+    with open(os.path.join(ROOT, "tests", "golden", "synthetic.json")) as fh:
+        g = json.load(fh)[name]
+    path = os.path.join(tmp, name + "_cpu.lp")
+    (instances.write_ap if g["kind"] == "ap" else instances.write_kp)(path, g["n"], g["k"], g["seed"])
+    model = read_model(path)
+    t = time.perf_counter()
+    cpu_rows = ao.pareto_front(model, ao.MilpOracle(model))
+    cpu_s = time.perf_counter() - t
+    ctx = mb.Context(mb.Problem(path), device=device, stream=stream)
+    t = time.perf_counter()
+    gpu_rows = ctx.pareto_front()
+    gpu_s = time.perf_counter() - t
+    ctx.close()
+    want = [tuple(r) for r in g["rows"]]
+    return {"instance": name, "cpu_seconds": cpu_s, "cpu_kind": "port (oracle generator + HiGHS milp, 1 core, -t 1; NOT CPLEX)",
+            "gpu_seconds": gpu_s, "front": len(want), "cpu_matches_golden": [tuple(r) for r in cpu_rows] == want,
+            "gpu_matches_golden": gpu_rows == want}
+
+
+def synthetic_front(name, strips, device, tmp):
+    """Pareto front of a synthetic instance with the EPP strips of every level sharded over the ranks
+    (one rank per GPU, NCCL all-gather of the points between levels) and solved concurrently inside a rank;
+    checked against the committed oracle front.  Time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from moip_aira_b200 import aira, instances
+    with open(os.path.join(ROOT, "tests", "golden", "synthetic.json")) as fh:
+        g = json.load(fh)[name]
+    path = os.path.join(tmp, name + ".lp")
+    (instances.write_ap if g["kind"] == "ap" else instances.write_kp)(path, g["n"], g["k"], g["seed"])
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    d = aira.Dist(torch.device("cuda", device) if world > 1 else None)
+    be = aira.GpuBackend(path, device=device)
+    d.barrier(); torch.cuda.synchronize()
+    t = time.perf_counter()
+    front = aira.epp_front(be, d, strips, False)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device="cuda")
+    ips = torch.tensor([float(be.ip_count())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ips, op=dist.ReduceOp.SUM)
+    return {"seconds": float(dt.item()), "front": len(front), "matches_golden": [list(r) for r in front] == g["rows"],
+            "ips": int(ips.item()), "workers_per_gpu": be.workers, "n_gpus": world}
 
 
 def time_to_front(mb, device, stream):

@@ -8,7 +8,8 @@ CPLEX.  Without --split one worker with the identity permutation runs on this ra
 inter-worker bound protocol of -t N > 1 is not re-hosted yet: SURVEY.md section 8f-3; the front is the
 same).  With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded over the ranks
 of a torch.distributed job (one rank per GPU, `torchrun --nproc-per-node G`), with an all-gather of
-the points found between levels; a single process solves the strips one after another.
+the points found between levels; inside a rank the strips run concurrently on a pool of solver
+contexts (MOIP_WORKERS host threads, default 12) that share the GPU.
 """
 from __future__ import annotations
 
@@ -65,29 +66,40 @@ class Dist:
 
 # ------------------------------------------------------------------------------------ backends
 class GpuBackend:
-    """Product backend: one solver context on this rank's B200."""
+    """Product backend on this rank's B200: one solver context for the sequential generator, a pool of
+    `workers` contexts (one host thread each, reference src/aira.cpp:1920-1933) for the EPP strips."""
 
-    def __init__(self, path, device=0, stream=None):
+    def __init__(self, path, device=0, stream=None, workers=None):
         import moip_aira_b200 as mb
         self.mb = mb
+        self.device, self.stream = device, stream
         self.problem = mb.Problem(path)
-        self.ctx = mb.Context(self.problem, device=device, stream=stream)
         self.k = self.problem.objcnt
         self.sense = self.problem.objsen
+        self.workers = max(1, int(os.environ.get("MOIP_WORKERS", "12")) if workers is None else int(workers))
+        self._ctx = None
+        self._pool = None
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = self.mb.Context(self.problem, device=self.device, stream=self.stream)
+        return self._ctx
+
+    @property
+    def pool(self):
+        if self._pool is None:
+            self._pool = self.mb.WorkerPool(self.problem, self.device, self.workers)
+        return self._pool
 
     def get_limit(self, obj, rhs):
-        st, res = self.ctx.get_limit(obj, rhs)
+        st, res = self.pool.get_limit(obj, rhs)
         return res
 
     def run_strips(self, n_obj, strips):
-        """The strips this rank owns at one EPP level, sharing `here`/`infeasibles` like the reference."""
-        mb = self.mb
-        here, inf = mb.Solutions(self.ctx), mb.Solutions(self.ctx)
-        for t, (a, b) in strips:
-            w = mb.make_worker(self.k, n_obj=n_obj, split=True, split_start=a, split_stop=b, wid=t)
-            self.ctx.optimise(w, here, inf)
-        rows = [here.get(i) for i in range(len(here))]
-        return [tuple(r[2]) for r in rows if not r[1]]
+        """The strips this rank owns at one EPP level, solved concurrently and sharing `here`/`infeasibles`
+        like the reference's threads."""
+        return self.pool.run_strips(n_obj, [s for _, s in strips])
 
     def sequential_front(self):
         return self.ctx.pareto_front()
@@ -96,7 +108,12 @@ class GpuBackend:
         return self.mb.split_strips(self.sense, biggest, smallest, num_threads, split_normal)
 
     def ip_count(self):
-        return self.ctx.stats()["ip_solved"]
+        n = 0
+        if self._ctx is not None:
+            n += self._ctx.stats()["ip_solved"]
+        if self._pool is not None:
+            n += self._pool.stats()["ip_solved"]
+        return n
 
 
 def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):

@@ -115,7 +115,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->root_x.assign(M.k, {});
   c->root_y.assign(M.k, {});
   c->bb_batch = env_int("MOIP_BB_BATCH", 0);
-  c->bb_max_iter = env_int("MOIP_BB_MAX_ITER", 3000);
+  c->bb_max_iter = env_int("MOIP_BB_MAX_ITER", 0);
   c->bb_eps = env_double("MOIP_BB_EPS", 1e-5);
   c->bb_check = env_int("MOIP_BB_CHECK", 32);
   c->norm_every = env_int("MOIP_NORM_EVERY", 16);
@@ -506,8 +506,14 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   std::vector<BranchOp> ops;
   std::vector<int> to_free;
   bool first_round = true;
+  // Node LPs are cut short: a round is as slow as its slowest LP, and a weaker (still valid) bound only costs
+  // nodes.  Measured optimum of the cap (tools/probe_synth.py): 3AP n=12 / 20 / 30 (144 / 400 / 900 columns) are
+  // fastest at about 200 / 300 / 600 iterations, the knapsacks at 200-300: cap = 20 sqrt(n), at least 200.  Only the
+  // cold root LP of an objective (no warm start yet) runs long; every later root starts from its iterate.
+  const bool cold_root = (int)root_x[cost].size() != n;
+  const int lp_cap = bb_max_iter > 0 ? bb_max_iter : std::min(2000, std::max(200, (int)(20.0 * std::sqrt((double)n))));
   LpParams lp{};
-  lp.eps = bb_eps; lp.max_iter = bb_max_iter; lp.check_every = bb_check; lp.fixed_iters = 0;
+  lp.eps = bb_eps; lp.max_iter = cold_root ? std::max(lp_cap, 20000) : lp_cap; lp.check_every = bb_check; lp.fixed_iters = 0;
   lp.norm_every = norm_every > 0 ? norm_every : 1; lp.cutoff_slack = 1.0 - 1e-6; lp.int_obj = 1;
 
   auto prunable = [&](double bound) {
@@ -613,6 +619,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       MOIP_CUDA(cudaStreamSynchronize(stream));
       inc_val = best_val; have_inc = true;
     }
+    if (first_round && cold_root) lp.max_iter = lp_cap;
     if (first_round && flag[0] == 0) {   // remember the root iterate as warm start for the next IP on this objective
       root_x[cost].resize(n); root_y[cost].resize(m);
       MOIP_CUDA(cudaMemcpyAsync(root_x[cost].data(), pool.wx + (size_t)ids[0] * n, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));

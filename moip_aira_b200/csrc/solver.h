@@ -108,7 +108,7 @@ struct moip_ctx {
   std::vector<std::vector<double>> root_x, root_y;   // warm start of the root per objective
   // tunables (env MOIP_*)
   int bb_batch = 0;            // 0 = SMs * occupancy
-  int bb_max_iter = 3000;
+  int bb_max_iter = 0;            // node-LP iteration cap; 0 = 20 sqrt(n), at least 200 (see solve_ip)
   double bb_eps = 1e-5;
   int bb_check = 32;
   int norm_every = 1;

@@ -3,6 +3,7 @@ include/moip_b200.h; the checker is the oracle (oracle/), the golden fronts of t
 Examples (tests/golden/examples.json) and -- for K3 -- the reference's own compiled Solutions::find
 (oracle/_ref/libaira_ref.so)."""
 import ctypes as C
+import json
 import os
 
 import numpy as np
@@ -326,6 +327,35 @@ def test_front_pool_matches_golden_out(mb, examples, stem, threads, normal, work
     assert front == e["rows"] and len(front) == e["count"]
     st = pool.stats()
     assert st["ip_solved"] > 0 and st["kernel_launches"] > 0
+    pool.close()
+
+
+def _synthetic_case(name, tmp_path):
+    from moip_aira_b200 import instances
+    with open(os.path.join(os.path.dirname(__file__), "golden", "synthetic.json")) as fh:
+        g = json.load(fh)[name]
+    path = str(tmp_path / f"{name}.lp")
+    (instances.write_ap if g["kind"] == "ap" else instances.write_kp)(path, g["n"], g["k"], g["seed"])
+    return path, [tuple(r) for r in g["rows"]]
+
+
+@pytest.mark.parametrize("name", ["ap3_8_1", "ap3_10_1", "ap4_7_2", "ap2_20_3", "kp4_20_1", "kp2_80_5"])
+def test_front_synthetic_golden_sequential(mb, tmp_path, name):
+    """Synthetic AP / KP instances of SURVEY.md 8d (items 4-5): the front of the default (-t 1) run equals the
+    front the CPU oracle computed (tests/golden/make_synthetic.py: restated generator + HiGHS, knapsacks
+    cross-checked by a solver-free DP)."""
+    path, want = _synthetic_case(name, tmp_path)
+    ctx = mb.Context(mb.Problem(path))
+    assert ctx.pareto_front() == want
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,strips,workers", [("ap3_12_1", 12, 12), ("ap3_15_1", 12, 12), ("kp4_25_1", 8, 8), ("kp3_40_1", 12, 6)])
+def test_front_synthetic_golden_pool(mb, tmp_path, name, strips, workers):
+    """Same, larger instances, EPP strips solved concurrently on one GPU (--split -t strips)."""
+    path, want = _synthetic_case(name, tmp_path)
+    pool = mb.WorkerPool(mb.Problem(path), 0, workers)
+    assert pool.pareto_front(strips) == want
     pool.close()
 
 

@@ -125,3 +125,24 @@ def test_pdhg_port_agrees_with_highs():
     assert np.all(np.abs(r["primal_obj"][ok] - obj[ok]) <= 1e-6 * np.maximum(1, np.abs(obj[ok])))
     assert np.all(r["status"][st == 2] == 3)
     assert np.all(r["dual_bound"][ok] <= obj[ok] + 1e-6 * np.maximum(1, np.abs(obj[ok])))
+
+
+def test_synthetic_golden_against_bruteforce():
+    """tests/golden/synthetic.json (made by the HiGHS-driven restatement) agrees with solver-free enumeration
+    where that is cheap: 3-objective assignment n=8 (8! permutations)."""
+    import json
+    from oracle import aira_oracle as ao
+    from oracle.lpformat import synthetic_ap
+    with open(os.path.join(os.path.dirname(__file__), "golden", "synthetic.json")) as fh:
+        g = json.load(fh)
+    model = synthetic_ap(8, 3, 1)
+    want = ao.brute_force_front(model, ao.FeasibleSet(model))
+    assert [tuple(r) for r in g["ap3_8_1"]["rows"]] == [tuple(r) for r in want]
+    for name, v in g.items():       # every stored front is sorted like the reference prints it and has no dominated row
+        rows = [tuple(r) for r in v["rows"]]
+        assert rows == sorted(set(rows), key=lambda r: tuple(-x for x in r)), name
+        sgn = 1 if v["kind"] == "ap" else -1
+        R = np.array(rows) * sgn
+        for i in range(0, len(R), max(1, len(R) // 40)):
+            dom = np.all(R <= R[i], axis=1) & np.any(R < R[i], axis=1)
+            assert not dom.any(), name
