@@ -100,6 +100,8 @@ std::mutex& launch_cfg_mutex();
 
 int launch_k1_any(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);   // best path the model allows
 int launch_k1_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
+bool k1_small_applies(const DevModel& dm);   // all rows dense, n <= 64: 8 lanes per node (k1_small.cu)
+int launch_k1_small(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_expand_masks(const DevModel& dm, int B, const uint32_t* masks, int mask_words, int* lb, int* ub,
@@ -126,7 +128,7 @@ int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queri
 // K4
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub,
                     int* xr /*[B][3][n]*/, long long* obj_out /*[B][3][k]*/, unsigned char* feasible_out /*[B][3]*/,
-                    cudaStream_t st);
+                    int* first_free /*[B][3]: first unfixed column, its lb, ub (or nullptr)*/, cudaStream_t st);
 int launch_k4(const DevModel& dm, int B, const int* x, const double* rhs, long long* obj_out,
               unsigned char* feasible_out, cudaStream_t st);
 

@@ -1,5 +1,6 @@
-// K1 dispatch: register-resident path (k1_reg.cuh) when the model fits it, else the shared-memory
-// fast path (k1_fast.cu), else the generic kernel (k1_pdhg.cu).
+// K1 dispatch: register-resident path (k1_reg.cuh) when the model fits it, the 8-lanes-per-node path
+// (k1_small.cu) for small all-dense models, else the shared-memory fast path (k1_fast.cu), else the generic
+// kernel (k1_pdhg.cu).
 #include "device.h"
 
 namespace moip {
@@ -23,6 +24,7 @@ int launch_k1_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int n
 
 int launch_k1_any(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (dm.reg_ok) return launch_k1_reg(dm, b, p, num_sms, st);
+  if (k1_small_applies(dm)) return launch_k1_small(dm, b, p, num_sms, st);
   if (dm.fast_ok) return launch_k1_fast(dm, b, p, num_sms, st);
   return launch_k1(dm, b, p, num_sms, st);
 }

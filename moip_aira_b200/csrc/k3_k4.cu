@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(128) k4_verify_kernel(const DevModel dm, int B
 // each candidate exactly; one warp per (node, candidate).  Feeds the incumbent search of the B&B.
 __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm, int B, const int* slot, const double* wx,
                                                               const int* lb, const int* ub, int* xr, long long* obj_out,
-                                                              unsigned char* feasible_out) {
+                                                              unsigned char* feasible_out, int* first_free) {
   const int lane = threadIdx.x & 31;
   const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -125,10 +125,13 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
     const size_t srow = slot ? (size_t)slot[node] : (size_t)node;
     int* xp = xr + (size_t)w * n;
     long long obj[MOIP_MAX_OBJ] = {0, 0, 0, 0};
+    int ff = INT_MAX;                     // first column that is not fixed yet (fallback branching column)
     for (int j = lane; j < n; j += 32) {
       const double v = wx[srow * n + j];
       int r = mode == 0 ? (int)llrint(v) : mode == 1 ? (int)floor(v + 1e-6) : (int)ceil(v - 1e-6);
-      r = max(lb[srow * n + j], min(ub[srow * n + j], r));
+      const int lj = lb[srow * n + j], uj = ub[srow * n + j];
+      if (lj < uj && ff == INT_MAX) ff = j;
+      r = max(lj, min(uj, r));
       xp[j] = r;
 #pragma unroll
       for (int o = 0; o < MOIP_MAX_OBJ; ++o)
@@ -144,6 +147,15 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
       a = warp_sum_ll(a);
       if (a < dm.ri_lo[i] || a > dm.ri_hi[i]) bad = 1;
     }
+    if (first_free && mode == 0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ff = min(ff, __shfl_xor_sync(0xffffffffu, ff, o));
+      if (lane == 0) {
+        first_free[(size_t)node * 3] = ff == INT_MAX ? -1 : ff;
+        first_free[(size_t)node * 3 + 1] = ff == INT_MAX ? 0 : lb[srow * n + ff];
+        first_free[(size_t)node * 3 + 2] = ff == INT_MAX ? 0 : ub[srow * n + ff];
+      }
+    }
     if (lane == 0) {
       feasible_out[w] = bad ? 0 : 1;
       for (int o = 0; o < dm.k; ++o) obj_out[(size_t)w * dm.k + o] = obj[o];
@@ -154,11 +166,11 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
 }  // namespace
 
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub, int* xr,
-                    long long* obj_out, unsigned char* feasible_out, cudaStream_t st) {
+                    long long* obj_out, unsigned char* feasible_out, int* first_free, cudaStream_t st) {
   if (B <= 0) return MOIP_OK;
   int blocks = (B * 3 + 3) / 4;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out);
+  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out, first_free);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }

@@ -495,7 +495,9 @@ int finalize_model(Model& M, std::string& err) {
   }
   // ---- fast-kernel image ----------------------------------------------------------------------
   {
-    const int long_thr = std::max(32, n / 8);
+    // small models with few rows (knapsacks): every row rides in the column pass, which is what k1_small.cu needs
+    const bool all_dense = n <= 64 && k + ms <= 5;
+    const int long_thr = all_dense ? 0 : std::max(32, n / 8);
     std::vector<int> shortr, longr;
     for (int i = 0; i < ms; ++i) ((M.a_ptr[i + 1] - M.a_ptr[i]) > long_thr ? longr : shortr).push_back(i);
     M.msS = (int)shortr.size(); M.nL = (int)longr.size(); M.KD = k + M.nL;

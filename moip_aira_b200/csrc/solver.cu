@@ -126,6 +126,10 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
 
 extern "C" void moip_ctx_destroy(moip_ctx* c) {
   if (!c) return;
+  if (c->prof_t[3] > 0)
+    std::fprintf(stderr, "moip_b200: %.0f B&B rounds (%.1f nodes each): enqueue %.1f us, wait for the device %.1f us, host %.1f us per round\n",
+                 c->prof_t[3], c->prof_t[4] / c->prof_t[3], 1e6 * c->prof_t[0] / c->prof_t[3], 1e6 * c->prof_t[1] / c->prof_t[3],
+                 1e6 * c->prof_t[2] / c->prof_t[3]);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (void* p : c->model_allocs) cudaFree(p);
@@ -140,7 +144,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   c->r_wx.release(); c->r_wy.release(); c->r_x.release(); c->r_y.release(); c->r_pobj.release();
   c->r_dbound.release(); c->r_bval.release(); c->r_rhs.release(); c->r_cutoff.release();
   c->r_leaf.release(); c->r_olo.release(); c->r_ohi.release(); c->r_cobj.release(); c->r_cfeas.release();
-  c->r_ops.release(); c->h_round.release();
+  c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release();
   delete c;
 }
 
@@ -464,26 +468,34 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   int Bmax = bb_batch > 0 ? bb_batch : num_sms * (dm.n <= 64 ? 16 : 4);
   if (ensure_pool(std::max(256, 4 * Bmax))) return MOIP_ERR_CUDA;
   int rc = 0;
-  rc |= r_ids.ensure((size_t)Bmax + 1); rc |= r_flag.ensure(Bmax); rc |= r_lb.ensure((size_t)Bmax * n); rc |= r_ub.ensure((size_t)Bmax * n);
-  rc |= r_status.ensure(Bmax); rc |= r_iters.ensure(Bmax); rc |= r_branch.ensure((size_t)3 * Bmax); rc |= r_xr.ensure((size_t)Bmax * 3 * n);
-  rc |= r_counter.ensure(1); rc |= r_wx.ensure((size_t)Bmax * n); rc |= r_wy.ensure((size_t)Bmax * m);
-  rc |= r_x.ensure((size_t)Bmax * n); rc |= r_y.ensure((size_t)Bmax * m); rc |= r_pobj.ensure(Bmax); rc |= r_dbound.ensure(Bmax);
-  rc |= r_bval.ensure((size_t)3 * Bmax); rc |= r_rhs.ensure(k); rc |= r_cutoff.ensure(1); rc |= r_leaf.ensure((size_t)Bmax * k);
-  rc |= r_olo.ensure(k); rc |= r_ohi.ensure(k); rc |= r_cobj.ensure((size_t)Bmax * 3 * k); rc |= r_cfeas.ensure((size_t)Bmax * 3);
-  rc |= r_ops.ensure((size_t)8 * Bmax);
-  // packed D2H layout per round
-  const size_t off_flag = 0, off_status = off_flag + sizeof(int) * Bmax, off_iters = off_status + sizeof(int) * Bmax,
-               off_branch = off_iters + sizeof(int) * Bmax, off_dbound = off_branch + sizeof(int) * 3 * Bmax + 8,
-               off_bval = off_dbound + sizeof(double) * Bmax, off_leaf = off_bval + sizeof(double) * 3 * Bmax,
-               off_cobj = off_leaf + sizeof(long long) * Bmax * k, off_cfeas = off_cobj + sizeof(long long) * Bmax * 3 * k,
-               off_end = off_cfeas + (size_t)Bmax * 3;
-  rc |= h_round.ensure(off_end + 64);
+  // One round = one H2D block in, one D2H block out (both pinned on the host).  The arrays of a round are laid
+  // out back to back for the round's own batch size B, so that a single copy moves exactly what is needed.
+  auto up8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+  struct InLayout { size_t ids, cost, olo, ohi, cutoff, rhs, end; };
+  struct OutLayout { size_t flag, status, iters, branch, ff, dbound, bval, leaf, cobj, cfeas, end; };
+  auto in_layout = [&](int B) {
+    InLayout L;
+    L.ids = 0; L.cost = up8(sizeof(int) * B); L.olo = L.cost + 8; L.ohi = L.olo + sizeof(long long) * k;
+    L.cutoff = L.ohi + sizeof(long long) * k; L.rhs = L.cutoff + 8; L.end = L.rhs + sizeof(double) * k;
+    return L;
+  };
+  auto out_layout = [&](int B) {
+    OutLayout L;
+    L.flag = 0; L.status = up8(L.flag + sizeof(int) * B); L.iters = up8(L.status + sizeof(int) * B);
+    L.branch = up8(L.iters + sizeof(int) * B); L.ff = up8(L.branch + sizeof(int) * 3 * B);
+    L.dbound = up8(L.ff + sizeof(int) * 3 * B);
+    L.bval = L.dbound + sizeof(double) * B; L.leaf = L.bval + sizeof(double) * 3 * B;
+    L.cobj = L.leaf + sizeof(long long) * B * k; L.cfeas = L.cobj + sizeof(long long) * B * 3 * k;
+    L.end = up8(L.cfeas + (size_t)B * 3);
+    return L;
+  };
+  rc |= r_in.ensure(in_layout(Bmax).end); rc |= r_out.ensure(out_layout(Bmax).end);
+  rc |= h_in.ensure(in_layout(Bmax).end); rc |= h_round.ensure(out_layout(Bmax).end);
+  rc |= r_xr.ensure((size_t)Bmax * 3 * n); rc |= r_counter.ensure(1); rc |= r_pobj.ensure(Bmax);
+  rc |= r_ops.ensure((size_t)8 * Bmax); rc |= h_ops.ensure((size_t)8 * Bmax);
   if (rc) return MOIP_ERR_CUDA;
   PoolView pool{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
 
-  MOIP_CUDA(cudaMemcpyAsync(r_rhs.p, srhs, sizeof(double) * k, cudaMemcpyHostToDevice, stream));
-  MOIP_CUDA(cudaMemcpyAsync(r_ids.p + Bmax, &cost, sizeof(int), cudaMemcpyHostToDevice, stream));
-  MOIP_CUDA(cudaStreamSynchronize(stream));   // srhs / cost are caller stack memory
   // root node
   std::vector<OpenNode> open;
   {
@@ -520,6 +532,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     return have_inc && bound > -HUGE_VAL && std::ceil(bound - 1e-6) >= (double)inc_val;
   };
 
+  const bool prof = std::getenv("MOIP_PROFILE_ROUNDS") != nullptr;
   while (!open.empty()) {
     // ---- select the batch: dive (deepest first) until an incumbent exists, then best bound first
     if (have_inc)
@@ -550,43 +563,62 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       if (M.sense == 0) phi[cost] = std::min(phi[cost], inc_val - 1);
       else plo[cost] = std::max(plo[cost], -inc_val + 1);
     }
-    MOIP_CUDA(cudaMemcpyAsync(r_ids.p, ids.data(), sizeof(int) * B, cudaMemcpyHostToDevice, stream));
-    MOIP_CUDA(cudaMemcpyAsync(r_olo.p, plo.data(), sizeof(long long) * k, cudaMemcpyHostToDevice, stream));
-    MOIP_CUDA(cudaMemcpyAsync(r_ohi.p, phi.data(), sizeof(long long) * k, cudaMemcpyHostToDevice, stream));
-    double cut = have_inc ? (double)inc_val : HUGE_VAL;
-    MOIP_CUDA(cudaMemcpyAsync(r_cutoff.p, &cut, sizeof(double), cudaMemcpyHostToDevice, stream));
-    // (the H2D sources above are host vectors/locals that stay alive until the sync below)
-    if (launch_k2_propagate(dm, pool, B, r_ids.p, r_olo.p, r_ohi.p, 16, r_flag.p, r_leaf.p, stream)) return MOIP_ERR_CUDA;
+    const InLayout LI = in_layout(B);
+    const OutLayout LO = out_layout(B);
+    const double tp0 = prof ? now_s() : 0.0;
+    {
+      unsigned char* hi = h_in.p;          // free again: the previous round synchronised after its last use
+      std::memcpy(hi + LI.ids, ids.data(), sizeof(int) * B);
+      std::memcpy(hi + LI.cost, &cost, sizeof(int));
+      std::memcpy(hi + LI.olo, plo.data(), sizeof(long long) * k);
+      std::memcpy(hi + LI.ohi, phi.data(), sizeof(long long) * k);
+      const double cut = have_inc ? (double)inc_val : HUGE_VAL;
+      std::memcpy(hi + LI.cutoff, &cut, sizeof(double));
+      std::memcpy(hi + LI.rhs, srhs, sizeof(double) * k);
+      MOIP_CUDA(cudaMemcpyAsync(r_in.p, hi, LI.end, cudaMemcpyHostToDevice, stream));
+    }
+    const int* d_ids = reinterpret_cast<const int*>(r_in.p + LI.ids);
+    const int* d_cost = reinterpret_cast<const int*>(r_in.p + LI.cost);
+    const long long* d_olo = reinterpret_cast<const long long*>(r_in.p + LI.olo);
+    const long long* d_ohi = reinterpret_cast<const long long*>(r_in.p + LI.ohi);
+    const double* d_cutoff = reinterpret_cast<const double*>(r_in.p + LI.cutoff);
+    const double* d_rhs = reinterpret_cast<const double*>(r_in.p + LI.rhs);
+    int* d_flag = reinterpret_cast<int*>(r_out.p + LO.flag);
+    int* d_status = reinterpret_cast<int*>(r_out.p + LO.status);
+    int* d_iters = reinterpret_cast<int*>(r_out.p + LO.iters);
+    int* d_branch = reinterpret_cast<int*>(r_out.p + LO.branch);
+    int* d_ff = reinterpret_cast<int*>(r_out.p + LO.ff);
+    double* d_dbound = reinterpret_cast<double*>(r_out.p + LO.dbound);
+    double* d_bval = reinterpret_cast<double*>(r_out.p + LO.bval);
+    long long* d_leaf = reinterpret_cast<long long*>(r_out.p + LO.leaf);
+    long long* d_cobj = reinterpret_cast<long long*>(r_out.p + LO.cobj);
+    unsigned char* d_cfeas = r_out.p + LO.cfeas;
+    if (launch_k2_propagate(dm, pool, B, d_ids, d_olo, d_ohi, 16, d_flag, d_leaf, stream)) return MOIP_ERR_CUDA;
     LpBatch b{};
-    b.B = B; b.rhs = r_rhs.p; b.lb = pool.lb; b.ub = pool.ub; b.slot = r_ids.p; b.rc_fix = have_inc ? 1 : 0;
+    b.B = B; b.rhs = d_rhs; b.lb = pool.lb; b.ub = pool.ub; b.slot = d_ids; b.rc_fix = have_inc ? 1 : 0;
     b.warm_x = pool.wx; b.warm_y = pool.wy; b.out_x = pool.wx; b.out_y = pool.wy;   // iterate returns to the node's slot
-    b.primal_obj = r_pobj.p; b.dual_bound = r_dbound.p; b.status = r_status.p; b.iters = r_iters.p;
-    b.branch_var = r_branch.p; b.branch_val = r_bval.p; b.skip = r_flag.p;
-    b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = r_cutoff.p; b.work_counter = r_counter.p;
-    b.cost_idx = r_ids.p + Bmax;   // one shared cost index, staged behind the ids (cost_stride = 0)
+    b.primal_obj = r_pobj.p; b.dual_bound = d_dbound; b.status = d_status; b.iters = d_iters;
+    b.branch_var = d_branch; b.branch_val = d_bval; b.skip = d_flag;
+    b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = d_cutoff; b.work_counter = r_counter.p;
+    b.cost_idx = d_cost;           // one shared cost index (cost_stride = 0)
     if (launch_k1_any(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
-    if (launch_k4_round(dm, B, r_ids.p, pool.wx, pool.lb, pool.ub, r_xr.p, r_cobj.p, r_cfeas.p, stream)) return MOIP_ERR_CUDA;
+    if (launch_k4_round(dm, B, d_ids, pool.wx, pool.lb, pool.ub, r_xr.p, d_cobj, d_cfeas, d_ff, stream)) return MOIP_ERR_CUDA;
     stats.kernel_launches += 3;
     unsigned char* H = h_round.p;
-    MOIP_CUDA(cudaMemcpyAsync(H + off_flag, r_flag.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_status, r_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_iters, r_iters.p, sizeof(int) * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_branch, r_branch.p, sizeof(int) * 3 * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_dbound, r_dbound.p, sizeof(double) * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_bval, r_bval.p, sizeof(double) * 3 * B, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_leaf, r_leaf.p, sizeof(long long) * B * k, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_cobj, r_cobj.p, sizeof(long long) * B * 3 * k, cudaMemcpyDeviceToHost, stream));
-    MOIP_CUDA(cudaMemcpyAsync(H + off_cfeas, r_cfeas.p, (size_t)B * 3, cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(H, r_out.p, LO.end, cudaMemcpyDeviceToHost, stream));
+    const double tp1 = prof ? now_s() : 0.0;
     MOIP_CUDA(cudaStreamSynchronize(stream));
-    const int* flag = (const int*)(H + off_flag);
-    const int* status = (const int*)(H + off_status);
-    const int* iters = (const int*)(H + off_iters);
-    const int* branch = (const int*)(H + off_branch);
-    const double* dbound = (const double*)(H + off_dbound);
-    const double* bval = (const double*)(H + off_bval);
-    const long long* leaf = (const long long*)(H + off_leaf);
-    const long long* cobj = (const long long*)(H + off_cobj);
-    const unsigned char* cfeas = H + off_cfeas;
+    const double tp2 = prof ? now_s() : 0.0;
+    const int* flag = (const int*)(H + LO.flag);
+    const int* status = (const int*)(H + LO.status);
+    const int* iters = (const int*)(H + LO.iters);
+    const int* branch = (const int*)(H + LO.branch);
+    const int* ffree = (const int*)(H + LO.ff);
+    const double* dbound = (const double*)(H + LO.dbound);
+    const double* bval = (const double*)(H + LO.bval);
+    const long long* leaf = (const long long*)(H + LO.leaf);
+    const long long* cobj = (const long long*)(H + LO.cobj);
+    const unsigned char* cfeas = H + LO.cfeas;
     // ---- incumbent candidates of this round (exactly evaluated on the device)
     int best_src = -1; bool best_is_leaf = false;
     long long best_val = inc_val;
@@ -651,12 +683,8 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       int vars[3]; double vals[3]; int nv = 0;
       for (int q = 0; q < levels; ++q) if (branch[3 * i + q] >= 0) { vars[nv] = branch[3 * i + q]; vals[nv] = bval[3 * i + q]; ++nv; }
       if (nv == 0) {
-        // LP point integral but not accepted: branch on the first unfixed column at its midpoint (rare path)
-        std::vector<int> nlb(n), nub(n);
-        MOIP_CUDA(cudaMemcpyAsync(nlb.data(), pool.lb + (size_t)nd.slot * n, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
-        MOIP_CUDA(cudaMemcpyAsync(nub.data(), pool.ub + (size_t)nd.slot * n, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
-        MOIP_CUDA(cudaStreamSynchronize(stream));
-        for (int j = 0; j < n; ++j) if (nlb[j] < nub[j]) { vars[0] = j; vals[0] = 0.5 * ((double)nlb[j] + (double)nub[j]); nv = 1; break; }
+        // LP point integral but not accepted: branch on the first unfixed column (found by K4) at its midpoint
+        if (ffree[3 * i] >= 0) { vars[0] = ffree[3 * i]; vals[0] = 0.5 * ((double)ffree[3 * i + 1] + (double)ffree[3 * i + 2]); nv = 1; }
         if (nv == 0) continue;   // fully fixed: K2 will have classified it as a leaf
       }
       const int nchild = 1 << nv;
@@ -680,12 +708,14 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       }
     }
     if (!ops.empty()) {
-      MOIP_CUDA(cudaMemcpyAsync(r_ops.p, ops.data(), sizeof(BranchOp) * ops.size(), cudaMemcpyHostToDevice, stream));
+      if (r_ops.ensure(ops.size()) || h_ops.ensure(ops.size())) return MOIP_ERR_CUDA;
+      std::memcpy(h_ops.p, ops.data(), sizeof(BranchOp) * ops.size());     // pinned; rewritten only after the next round's sync
+      MOIP_CUDA(cudaMemcpyAsync(r_ops.p, h_ops.p, sizeof(BranchOp) * ops.size(), cudaMemcpyHostToDevice, stream));
       if (launch_k2_branch(dm, pool, (int)ops.size(), r_ops.p, stream)) return MOIP_ERR_CUDA;
       stats.kernel_launches += 1;
-      MOIP_CUDA(cudaStreamSynchronize(stream));   // ops (host vector) is reused next round
     }
     for (int s : to_free) free_slots.push_back(s);
+    if (prof) { const double tp3 = now_s(); prof_t[0] += tp1 - tp0; prof_t[1] += tp2 - tp1; prof_t[2] += tp3 - tp2; prof_t[3] += 1; prof_t[4] += B; }
   }
   for (auto& nd : open) free_slots.push_back(nd.slot);
   if (have_inc) {

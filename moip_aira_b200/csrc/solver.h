@@ -105,6 +105,9 @@ struct moip_ctx {
   moip::DBuf<unsigned char> r_cfeas;
   moip::DBuf<moip::BranchOp> r_ops;
   moip::HBuf<unsigned char> h_round;    // packed D2H results of one round
+  moip::DBuf<unsigned char> r_in, r_out; // one H2D block in / one D2H block out per round (solve_ip)
+  moip::HBuf<unsigned char> h_in;
+  moip::HBuf<moip::BranchOp> h_ops;
   std::vector<std::vector<double>> root_x, root_y;   // warm start of the root per objective
   // tunables (env MOIP_*)
   int bb_batch = 0;            // 0 = SMs * occupancy
@@ -113,6 +116,8 @@ struct moip_ctx {
   int bb_check = 32;
   int norm_every = 1;
   int bb_levels = 3;           // max tree levels expanded per round while the device is under-filled
+
+  double prof_t[5] = {0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
   int ensure_pool(int slots);
   int alloc_slot();

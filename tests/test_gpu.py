@@ -153,16 +153,17 @@ def _lp_case(kind):
     from oracle.lpformat import synthetic_ap, synthetic_kp
     kind = kind.split("-")[0]
     k = 4 if kind.startswith("kp") else 3
-    if kind[-1] in "24" and kind[-2] == "k":        # e.g. ap16k4: 4 objectives
+    if kind[-1] in "234" and kind[-2] == "k":       # e.g. ap16k4: 4 objectives
         k = int(kind[-1]); kind = kind[:-2]
     size = int(kind[2:])
     return synthetic_ap(size, k, 1) if kind.startswith("ap") else synthetic_kp(size, k, 1)
 
 
-# K1 has three code paths: k1_fast (n <= 64), the register-resident k1_reg with NT x CPT = 128x2 (n <= 256),
-# 256x2 (n <= 512) and 256x4 (n <= 1024), and the generic kernel.
+# K1 code paths: k1_small (all rows dense, n <= 64: 8 lanes per node, CPT = 2 / 5 / 8 columns per lane), k1_fast (other
+# models with n <= 64), the register-resident k1_reg with NT x CPT = 128x2 (n <= 256), 256x2 (n <= 512) and 256x4
+# (n <= 1024), and the generic kernel.
 @pytest.mark.parametrize("kind,B", [("ap8", 24), ("kp40", 48), ("ap30", 16), ("ap12", 24), ("ap20", 16),
-                                    ("kp100", 32), ("ap16k4", 16), ("ap12k2", 16)])
+                                    ("kp100", 32), ("ap16k4", 16), ("ap12k2", 16), ("kp12k3", 64), ("kp50k2", 32), ("kp64", 32)])
 def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B, monkeypatch):
     """LP relaxation objectives within 1e-6 relative of HiGHS (stand-in: the reference pins no LP value)
     and of the C restatement; infeasible nodes are recognised; the dual bound is a valid bound."""
@@ -195,7 +196,7 @@ def test_k1_lp_objective_vs_highs_and_port(mb, tmp_path, kind, B, monkeypatch):
     ctx.close()
 
 
-@pytest.mark.parametrize("kind", ["ap8", "ap12", "ap30", "kp100"])
+@pytest.mark.parametrize("kind", ["ap8", "ap12", "ap30", "kp100", "kp40", "kp12k3", "kp50k2"])
 def test_k1_fixed_iterations_match_port(mb, tmp_path, kind, monkeypatch):
     """Same arithmetic as the C restatement: after a fixed number of iterations the iterates agree."""
     from oracle import pdhg_oracle as po
