@@ -135,9 +135,17 @@ def test_synthetic_golden_against_bruteforce():
     from oracle.lpformat import synthetic_ap
     with open(os.path.join(os.path.dirname(__file__), "golden", "synthetic.json")) as fh:
         g = json.load(fh)
+    import itertools
     model = synthetic_ap(8, 3, 1)
-    want = ao.brute_force_front(model, ao.FeasibleSet(model))
-    assert [tuple(r) for r in g["ap3_8_1"]["rows"]] == [tuple(r) for r in want]
+    C = model.C.reshape(3, 8, 8)                       # cost of assigning row i to column j, per objective
+    perms = np.array(list(itertools.permutations(range(8))))
+    P = np.unique(np.rint(sum(C[:, i, perms[:, i]] for i in range(8))).astype(np.int64).T, axis=0)
+    keep = []                                         # np.unique sorts lexicographically: a later row never dominates an earlier one
+    for p in P:
+        if not any(all(q[i] <= p[i] for i in range(3)) for q in keep):
+            keep.append(tuple(int(v) for v in p))
+    want = sorted(keep, key=lambda r: tuple(-v for v in r))
+    assert [tuple(r) for r in g["ap3_8_1"]["rows"]] == want
     for name, v in g.items():       # every stored front is sorted like the reference prints it and has no dominated row
         rows = [tuple(r) for r in v["rows"]]
         assert rows == sorted(set(rows), key=lambda r: tuple(-x for x in r)), name
