@@ -29,6 +29,14 @@ void refsol_find_batch(void* h, int q, int k, const double* ips, int sense_is_ma
   for (int i = 0; i < q; ++i) out[i] = refsol_find(h, ips + (size_t)i * k, sense_is_max);
 }
 
+// timing entry: the reference's own Solutions::find on q queries, nothing else; returns the number of hits
+int refsol_find_count(void* h, int q, int k, const double* ips, int sense_is_max) {
+  Solutions* s = static_cast<Solutions*>(h);
+  int hits = 0;
+  for (int i = 0; i < q; ++i) hits += s->find(ips + (size_t)i * k, sense_is_max ? MAX : MIN) != nullptr;
+  return hits;
+}
+
 int refsol_size(void* h) {
   Solutions* s = static_cast<Solutions*>(h);
   int i = 0;
