@@ -112,10 +112,11 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   rc |= upload(c, M.lbI, &d.lbI);
   rc |= upload(c, M.ubI, &d.ubI);
   if (rc) { moip_ctx_destroy(c); return MOIP_ERR_CUDA; }
-  c->root_x.assign(M.k, {});
-  c->root_y.assign(M.k, {});
+  c->root_valid.assign(M.k, 0);
   c->bb_batch = env_int("MOIP_BB_BATCH", 0);
   c->bb_max_iter = env_int("MOIP_BB_MAX_ITER", 0);
+  c->bb_cap_lo = env_double("MOIP_BB_CAP_LO", 0.38);
+  c->bb_cap_hi = env_double("MOIP_BB_CAP_HI", 0.50);
   c->bb_eps = env_double("MOIP_BB_EPS", 1e-5);
   c->bb_check = env_int("MOIP_BB_CHECK", 32);
   c->norm_every = env_int("MOIP_NORM_EVERY", 16);
@@ -127,8 +128,8 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
 extern "C" void moip_ctx_destroy(moip_ctx* c) {
   if (!c) return;
   if (c->prof_t[3] > 0)
-    std::fprintf(stderr, "moip_b200: %.0f B&B rounds (%.1f nodes each): enqueue %.1f us, wait for the device %.1f us, host %.1f us per round\n",
-                 c->prof_t[3], c->prof_t[4] / c->prof_t[3], 1e6 * c->prof_t[0] / c->prof_t[3], 1e6 * c->prof_t[1] / c->prof_t[3],
+    std::fprintf(stderr, "moip_b200: %.0f B&B rounds (%.1f nodes each), node-LP cap %d (%.0f %% of the LPs hit it): enqueue %.1f us, wait for the device %.1f us, host %.1f us per round\n",
+                 c->prof_t[3], c->prof_t[4] / c->prof_t[3], c->bb_max_iter > 0 ? c->bb_max_iter : c->lp_cap_dyn, 100.0 * c->prof_t[6] / std::max(1.0, c->prof_t[5]), 1e6 * c->prof_t[0] / c->prof_t[3], 1e6 * c->prof_t[1] / c->prof_t[3],
                  1e6 * c->prof_t[2] / c->prof_t[3]);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
@@ -144,7 +145,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   c->r_wx.release(); c->r_wy.release(); c->r_x.release(); c->r_y.release(); c->r_pobj.release();
   c->r_dbound.release(); c->r_bval.release(); c->r_rhs.release(); c->r_cutoff.release();
   c->r_leaf.release(); c->r_olo.release(); c->r_ohi.release(); c->r_cobj.release(); c->r_cfeas.release();
-  c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release();
+  c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release(); c->d_inc.release(); c->d_root_x.release(); c->d_root_y.release();
   delete c;
 }
 
@@ -459,6 +460,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   bool have_inc = false;
   long long inc_val = LLONG_MAX;
   std::vector<int> inc_x;
+  bool inc_on_device = false;
   if (inc_x_in && (int)inc_x_in->size() == n) {
     long long v = 0;
     for (int j = 0; j < n; ++j) v += M.ci[(size_t)cost * n + j] * (long long)(*inc_x_in)[j];
@@ -493,6 +495,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   rc |= h_in.ensure(in_layout(Bmax).end); rc |= h_round.ensure(out_layout(Bmax).end);
   rc |= r_xr.ensure((size_t)Bmax * 3 * n); rc |= r_counter.ensure(1); rc |= r_pobj.ensure(Bmax);
   rc |= r_ops.ensure((size_t)8 * Bmax); rc |= h_ops.ensure((size_t)8 * Bmax);
+  rc |= d_inc.ensure(n); rc |= d_root_x.ensure((size_t)k * n); rc |= d_root_y.ensure((size_t)k * m);
   if (rc) return MOIP_ERR_CUDA;
   PoolView pool{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
 
@@ -504,9 +507,9 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     pool = PoolView{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
     MOIP_CUDA(cudaMemcpyAsync(pool.lb + (size_t)s * n, dm.lbI, sizeof(int) * n, cudaMemcpyDeviceToDevice, stream));
     MOIP_CUDA(cudaMemcpyAsync(pool.ub + (size_t)s * n, dm.ubI, sizeof(int) * n, cudaMemcpyDeviceToDevice, stream));
-    if ((int)root_x[cost].size() == n) {
-      MOIP_CUDA(cudaMemcpyAsync(pool.wx + (size_t)s * n, root_x[cost].data(), sizeof(double) * n, cudaMemcpyHostToDevice, stream));
-      MOIP_CUDA(cudaMemcpyAsync(pool.wy + (size_t)s * m, root_y[cost].data(), sizeof(double) * m, cudaMemcpyHostToDevice, stream));
+    if (root_valid[cost]) {     // the root iterate of the last IP on this objective (kept on the device)
+      MOIP_CUDA(cudaMemcpyAsync(pool.wx + (size_t)s * n, d_root_x.p + (size_t)cost * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+      MOIP_CUDA(cudaMemcpyAsync(pool.wy + (size_t)s * m, d_root_y.p + (size_t)cost * m, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
     } else {
       MOIP_CUDA(cudaMemsetAsync(pool.wx + (size_t)s * n, 0, sizeof(double) * n, stream));
       MOIP_CUDA(cudaMemsetAsync(pool.wy + (size_t)s * m, 0, sizeof(double) * m, stream));
@@ -519,11 +522,13 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   std::vector<int> to_free;
   bool first_round = true;
   // Node LPs are cut short: a round is as slow as its slowest LP, and a weaker (still valid) bound only costs
-  // nodes.  Measured optimum of the cap (tools/probe_synth.py): 3AP n=12 / 20 / 30 (144 / 400 / 900 columns) are
-  // fastest at about 200 / 300 / 600 iterations, the knapsacks at 200-300: cap = 20 sqrt(n), at least 200.  Only the
-  // cold root LP of an objective (no warm start yet) runs long; every later root starts from its iterate.
-  const bool cold_root = (int)root_x[cost].size() != n;
-  const int lp_cap = bb_max_iter > 0 ? bb_max_iter : std::min(2000, std::max(200, (int)(20.0 * std::sqrt((double)n))));
+  // nodes -- until the cap falls below what the LPs of this model need, where the node count explodes (2KP n=100:
+  // 8.0e6 nodes at 200 iterations, 2.3e5 at 400, 1.1e5 at 800).  The cap therefore follows the share of node LPs
+  // that hit it (kept between bb_cap_lo and bb_cap_hi of a round's LPs), starting from 20 sqrt(n); it is a property
+  // of the model and carries over from one IP to the next.  Only the cold root LP of an objective runs long.
+  const bool cold_root = !root_valid[cost];
+  if (lp_cap_dyn <= 0) lp_cap_dyn = std::min(2000, std::max(200, (int)(20.0 * std::sqrt((double)n))));
+  int lp_cap = bb_max_iter > 0 ? bb_max_iter : lp_cap_dyn;
   LpParams lp{};
   lp.eps = bb_eps; lp.max_iter = cold_root ? std::max(lp_cap, 20000) : lp_cap; lp.check_every = bb_check; lp.fixed_iters = 0;
   lp.norm_every = norm_every > 0 ? norm_every : 1; lp.cutoff_slack = 1.0 - 1e-6; lp.int_obj = 1;
@@ -644,19 +649,30 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
         }
       }
     }
-    if (best_src >= 0) {
-      inc_x.resize(n);
+    if (best_src >= 0) {         // the incumbent stays on the device until the IP is solved (no extra synchronise per round)
       const int* src = best_is_leaf ? pool.lb + (size_t)ids[best_src / 3] * n : r_xr.p + (size_t)best_src * n;
-      MOIP_CUDA(cudaMemcpyAsync(inc_x.data(), src, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
-      MOIP_CUDA(cudaStreamSynchronize(stream));
-      inc_val = best_val; have_inc = true;
+      MOIP_CUDA(cudaMemcpyAsync(d_inc.p, src, sizeof(int) * n, cudaMemcpyDeviceToDevice, stream));
+      inc_val = best_val; have_inc = true; inc_on_device = true;
     }
-    if (first_round && cold_root) lp.max_iter = lp_cap;
+    if (!(first_round && cold_root)) {   // cap controller
+      int solved = 0, capped = 0;
+      for (int i = 0; i < B; ++i)
+        if (flag[i] == 0) { ++solved; capped += status[i] == MOIP_LP_ITERLIMIT; }
+      cap_seen += solved; cap_hit += capped;
+      prof_t[5] += solved; prof_t[6] += capped;
+      if (bb_max_iter <= 0 && cap_seen >= 64) {
+        const double share = (double)cap_hit / (double)cap_seen;
+        if (share > bb_cap_hi) lp_cap_dyn = std::min(6000, lp_cap_dyn + lp_cap_dyn / 4 + 1);
+        else if (share < bb_cap_lo) lp_cap_dyn = std::max(100, lp_cap_dyn - lp_cap_dyn / 8);
+        cap_seen = 0; cap_hit = 0;
+      }
+      if (bb_max_iter <= 0) lp_cap = lp_cap_dyn;
+    }
+    lp.max_iter = lp_cap;
     if (first_round && flag[0] == 0) {   // remember the root iterate as warm start for the next IP on this objective
-      root_x[cost].resize(n); root_y[cost].resize(m);
-      MOIP_CUDA(cudaMemcpyAsync(root_x[cost].data(), pool.wx + (size_t)ids[0] * n, sizeof(double) * n, cudaMemcpyDeviceToHost, stream));
-      MOIP_CUDA(cudaMemcpyAsync(root_y[cost].data(), pool.wy + (size_t)ids[0] * m, sizeof(double) * m, cudaMemcpyDeviceToHost, stream));
-      MOIP_CUDA(cudaStreamSynchronize(stream));
+      MOIP_CUDA(cudaMemcpyAsync(d_root_x.p + (size_t)cost * n, pool.wx + (size_t)ids[0] * n, sizeof(double) * n, cudaMemcpyDeviceToDevice, stream));
+      MOIP_CUDA(cudaMemcpyAsync(d_root_y.p + (size_t)cost * m, pool.wy + (size_t)ids[0] * m, sizeof(double) * m, cudaMemcpyDeviceToDevice, stream));
+      root_valid[cost] = 1;
     }
     first_round = false;
     // ---- branch.  While the device is under-filled the tree is expanded several levels per round
@@ -719,6 +735,11 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   }
   for (auto& nd : open) free_slots.push_back(nd.slot);
   if (have_inc) {
+    if (inc_on_device) {
+      inc_x.resize(n);
+      MOIP_CUDA(cudaMemcpyAsync(inc_x.data(), d_inc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaStreamSynchronize(stream));
+    }
     out.status = MOIP_MIP_OPTIMAL;
     out.obj = (long long)sgn * inc_val;
     out.x = inc_x;

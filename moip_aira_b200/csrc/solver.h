@@ -108,16 +108,21 @@ struct moip_ctx {
   moip::DBuf<unsigned char> r_in, r_out; // one H2D block in / one D2H block out per round (solve_ip)
   moip::HBuf<unsigned char> h_in;
   moip::HBuf<moip::BranchOp> h_ops;
-  std::vector<std::vector<double>> root_x, root_y;   // warm start of the root per objective
+  moip::DBuf<double> d_root_x, d_root_y;            // [k][n] / [k][m] root iterate per objective (warm start of the next IP)
+  std::vector<char> root_valid;
+  moip::DBuf<int> d_inc;                            // incumbent of the IP being solved
   // tunables (env MOIP_*)
   int bb_batch = 0;            // 0 = SMs * occupancy
-  int bb_max_iter = 0;            // node-LP iteration cap; 0 = 20 sqrt(n), at least 200 (see solve_ip)
+  int bb_max_iter = 0;            // fixed node-LP iteration cap; 0 = controlled (see solve_ip)
+  double bb_cap_lo = 0.38, bb_cap_hi = 0.50;   // share of a round's LPs allowed to hit the cap
+  int lp_cap_dyn = 0;             // current cap
+  long long cap_seen = 0, cap_hit = 0;
   double bb_eps = 1e-5;
   int bb_check = 32;
   int norm_every = 1;
   int bb_levels = 3;           // max tree levels expanded per round while the device is under-filled
 
-  double prof_t[5] = {0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
+  double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
   int ensure_pool(int slots);
   int alloc_slot();
