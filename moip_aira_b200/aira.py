@@ -4,9 +4,9 @@
 
 Options, defaults, output-file naming and the `.out` layout follow the reference (options :159-188,
 naming :213-221, writer :252, :336-358).  `-c` (CPLEX threads) is accepted and ignored: there is no
-CPLEX.  Without --split one worker with the identity permutation runs on this rank's GPU (the
-inter-worker bound protocol of -t N > 1 is not re-hosted yet: SURVEY.md section 8f-3; the front is the
-same).  With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded over the ranks
+CPLEX.  -t 1 runs the sequential generator on this rank's GPU.  -t N > 1 without --split would be the
+reference's synergistic mode; its inter-worker bound protocol is not re-hosted, so the
+N workers run as N EPP strips instead (same front).  With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded over the ranks
 of a torch.distributed job (one rank per GPU, `torchrun --nproc-per-node G`), with an all-gather of
 the points found between levels; inside a rank the strips run concurrently on a pool of solver
 contexts (MOIP_WORKERS host threads, default 12) that share the GPU.
@@ -191,11 +191,15 @@ def main(argv=None, backend_factory=None):
         print("Error: at most 4 objectives are supported.", file=sys.stderr)
         return 2
     t0, c0 = time.monotonic(), time.process_time()
-    if args.split:
-        front = epp_front(be, dist, max(1, args.threads), args.split_normal)
+    if args.split or args.threads > 1 or dist.world > 1:
+        # -t N without --split is the reference's synergistic mode (N permutation workers exchanging bounds,
+        # src/aira.cpp:923-1552).  That protocol is not re-hosted; the N workers are run as N EPP strips instead,
+        # which yields the same front (only IP counts and timing differ, as they do between the reference's modes).
+        if not args.split and dist.rank == 0:
+            print("note: -t %d without --split: the workers run as EPP strips (same front; the bound-sharing "
+                  "protocol of the synergistic mode is not re-hosted)" % args.threads, file=sys.stderr)
+        front = epp_front(be, dist, max(1, args.threads, dist.world), args.split_normal)
     else:
-        if args.threads > 1 and dist.rank == 0:
-            print("note: -t > 1 without --split runs one worker (bound-sharing protocol not re-hosted)", file=sys.stderr)
         front = be.sequential_front()
     wall, cpu = time.monotonic() - t0, time.process_time() - c0
     if dist.rank == 0:

@@ -83,6 +83,9 @@ struct LpBatch {
   int cost_stride, rhs_stride;// 0 = all nodes share cost_idx[0] / rhs[0..k)
   const double* cutoff;       // device scalar (min-form); node stops once bound >= *cutoff - cutoff_slack
   int* work_counter;          // device int, zeroed before launch (dynamic node scheduling)
+  double* scratch;            // generic kernel, large models: per-CTA iterate storage in HBM (nullptr = shared memory)
+  size_t scratch_stride;      // doubles per CTA (k1_scratch_stride)
+  int scratch_slots;          // CTAs the scratch has room for
 };
 
 struct LpParams {
@@ -104,6 +107,7 @@ bool k1_small_applies(const DevModel& dm);   // all rows dense, n <= 64: 8 lanes
 int launch_k1_small(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
 int launch_k1(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
+size_t k1_scratch_stride(const DevModel& dm);   // > 0: the generic kernel needs LpBatch::scratch for this model
 int launch_expand_masks(const DevModel& dm, int B, const uint32_t* masks, int mask_words, int* lb, int* ub,
                         cudaStream_t st);
 

@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
   constexpr int NW = NT / 32;
   extern __shared__ double smem[];
   const int n = dm.n, ms = dm.ms, k = dm.k, m = dm.m, ellw = dm.ell_w;
-  double* x = smem;
+  // Large models (5n + 8m doubles beyond the 227 KB of an SM): the iterate of the node lives in a per-CTA scratch
+  // region in HBM / L2 instead of shared memory (streaming mode); only the reduction buffers stay on chip.
+  double* base = b.scratch ? b.scratch + (size_t)blockIdx.x * b.scratch_stride : smem;
+  double* x = base;
   double* xa = x + n;
   double* xbar = xa + n;
   double* l = xbar + n;
@@ -75,7 +78,7 @@ __global__ void __launch_bounds__(NT) k1_pdhg_kernel(const DevModel dm, const Lp
   double* sxt = sxa + m;
   double* lo = sxt + m;
   double* hi = lo + m;
-  double* redA = hi + m;        // NW*8
+  double* redA = b.scratch ? smem : hi + m;        // NW*8
   double* redB = redA + NW * 8; // NW*8
   double* redC = redB + NW * 8; // NW*8
   __shared__ int s_node;
@@ -368,7 +371,12 @@ __global__ void expand_masks_kernel(const DevModel dm, int B, const uint32_t* ma
 
 template <int NT>
 int launch_nt(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
-  const size_t smem = sizeof(double) * ((size_t)5 * dm.n + (size_t)8 * dm.m + (size_t)24 * (NT / 32));
+  const bool streaming = b.scratch != nullptr;
+  const size_t smem = sizeof(double) * ((streaming ? 0 : (size_t)5 * dm.n + (size_t)8 * dm.m) + (size_t)24 * (NT / 32));
+  if (!streaming && k1_scratch_stride(dm) != 0) {
+    std::fprintf(stderr, "moip_b200: node LP needs the streaming scratch (n=%d) but none was provided\n", dm.n);
+    return MOIP_ERR_LIMIT;
+  }
   static size_t configured = 0;
   std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
   if (smem > configured) {
@@ -379,8 +387,10 @@ int launch_nt(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_s
   int occ = 1;
   MOIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_pdhg_kernel<NT>, NT, smem));
   if (occ < 1) { std::fprintf(stderr, "moip_b200: node LP does not fit in shared memory (n=%d)\n", dm.n); return MOIP_ERR_LIMIT; }
+  if (streaming && occ > 4) occ = 4;
   long long grid = (long long)num_sms * occ;
   if (grid > b.B) grid = b.B;
+  if (streaming && grid > b.scratch_slots) grid = b.scratch_slots;
   if (grid < 1) grid = 1;
   k1_pdhg_kernel<NT><<<(unsigned)grid, NT, smem, st>>>(dm, b, p);
   MOIP_CUDA(cudaGetLastError());
@@ -388,6 +398,12 @@ int launch_nt(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_s
 }
 
 }  // namespace
+
+// doubles of per-CTA scratch the generic kernel needs when the iterate does not fit in shared memory (0 = fits)
+size_t k1_scratch_stride(const DevModel& dm) {
+  const size_t need = (size_t)5 * dm.n + (size_t)8 * dm.m;
+  return (need + 24 * 8) * sizeof(double) > 200 * 1024 ? ((need + 15) & ~(size_t)15) : 0;
+}
 
 int launch_k1(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (b.B <= 0) return MOIP_OK;

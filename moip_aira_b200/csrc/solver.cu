@@ -145,7 +145,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   c->r_wx.release(); c->r_wy.release(); c->r_x.release(); c->r_y.release(); c->r_pobj.release();
   c->r_dbound.release(); c->r_bval.release(); c->r_rhs.release(); c->r_cutoff.release();
   c->r_leaf.release(); c->r_olo.release(); c->r_ohi.release(); c->r_cobj.release(); c->r_cfeas.release();
-  c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release(); c->d_inc.release(); c->d_root_x.release(); c->d_root_y.release();
+  c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release(); c->d_inc.release(); c->d_root_x.release(); c->d_root_y.release(); c->k1_scratch.release();
   delete c;
 }
 
@@ -220,6 +220,7 @@ extern "C" int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params) {
   p.cutoff_slack = 0.0; p.int_obj = 0;
   c->stats.kernel_launches += 1;
   c->stats.node_lps += b.B;
+  if (c->attach_k1_scratch(b)) return MOIP_ERR_CUDA;
   return launch_k1_any(d, b, p, c->num_sms, c->stream);
 }
 
@@ -408,6 +409,18 @@ extern "C" int moip_verify_int64(moip_ctx* c, int B, const int32_t* x, const dou
 }
 
 // ------------------------------------------------------------------------------------ B&B
+// large models that run on the generic kernel keep the iterate of every resident CTA in HBM (streaming mode)
+int moip_ctx::attach_k1_scratch(moip::LpBatch& b) {
+  b.scratch = nullptr; b.scratch_stride = 0; b.scratch_slots = 0;
+  if (dm.reg_ok || dm.fast_ok) return MOIP_OK;
+  const size_t stride = k1_scratch_stride(dm);
+  if (stride == 0) return MOIP_OK;
+  const int slots = num_sms * 4;
+  if (k1_scratch.ensure(stride * (size_t)slots)) return MOIP_ERR_CUDA;
+  b.scratch = k1_scratch.p; b.scratch_stride = stride; b.scratch_slots = slots;
+  return MOIP_OK;
+}
+
 int moip_ctx::ensure_pool(int slots) {
   if (slots <= pool_slots) return MOIP_OK;
   int ns = pool_slots ? pool_slots : 256;
@@ -606,6 +619,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     b.branch_var = d_branch; b.branch_val = d_bval; b.skip = d_flag;
     b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = d_cutoff; b.work_counter = r_counter.p;
     b.cost_idx = d_cost;           // one shared cost index (cost_stride = 0)
+    if (attach_k1_scratch(b)) return MOIP_ERR_CUDA;
     if (launch_k1_any(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
     if (launch_k4_round(dm, B, d_ids, pool.wx, pool.lb, pool.ub, r_xr.p, d_cobj, d_cfeas, d_ff, stream)) return MOIP_ERR_CUDA;
     stats.kernel_launches += 3;

@@ -124,6 +124,8 @@ struct moip_ctx {
 
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
+  moip::DBuf<double> k1_scratch;   // streaming mode of the generic K1 kernel (models too large for shared memory)
+  int attach_k1_scratch(moip::LpBatch& b);
   int ensure_pool(int slots);
   int alloc_slot();
   int solve_ip(int cost, const double* srhs, const std::vector<int>* inc_x, moip::IpResult& out);

@@ -175,6 +175,18 @@ def test_aira_cli_epp_single_process(lib, examples, stem, tmp_path):
     assert parse_out(open(out).read()) == (e["rows"], e["count"])
 
 
+def test_aira_cli_threads_without_split_runs_strips(lib, examples, tmp_path):
+    """-t N without --split (the reference's synergistic mode): same front, computed as N EPP strips."""
+    from moip_aira_b200 import aira
+    from oracle.lpformat import parse_out
+    e = examples["3AP05"]
+    out = str(tmp_path / "o.out")
+    assert aira.main(["-p", e["path"], "-o", out, "-t", "4"], backend_factory=_OracleBackend) == 0
+    assert parse_out(open(out).read()) == (e["rows"], e["count"])
+    assert aira.main(["-p", e["path"], "-o", out], backend_factory=_OracleBackend) == 0      # -t 1: sequential generator
+    assert parse_out(open(out).read()) == (e["rows"], e["count"])
+
+
 _RANK_SCRIPT = r'''
 import os, sys
 sys.path.insert(0, {root!r})
