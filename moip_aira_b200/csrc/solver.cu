@@ -90,7 +90,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   rc |= upload(c, M.dr, &d.dr);
   rc |= upload(c, M.dc, &d.dc);
   d.fast_ok = M.fast_ok ? 1 : 0; d.msS = M.msS; d.nL = M.nL; d.KD = M.KD; d.RW = M.RW; d.ell2_w = M.ell2_w;
-  if (std::getenv("MOIP_K1_GENERIC")) d.fast_ok = 0;
+  if (std::getenv("MOIP_K1_GENERIC")) { d.fast_ok = 0; d.reg_ok = 0; }
   rc |= upload(c, M.rowell_val, &d.rowell_val);
   rc |= upload(c, M.rowell_col, &d.rowell_col);
   rc |= upload(c, M.ellT2_val, &d.ellT2_val);
@@ -100,7 +100,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   rc |= upload(c, M.colrec, &d.colrec);
   rc |= upload(c, M.rowrec, &d.rowrec);
   d.reg_ok = M.reg_ok ? 1 : 0; d.RWP = M.RWP; d.reg_lpr_log2 = M.reg_lpr_log2; d.reg_trips = M.reg_trips;
-  if (std::getenv("MOIP_K1_NOREG")) d.reg_ok = 0;
+  if (std::getenv("MOIP_K1_NOREG") || std::getenv("MOIP_K1_GENERIC")) d.reg_ok = 0;
   rc |= upload(c, M.colrec2, &d.colrec2);
   rc |= upload(c, M.dr_k, &d.dr_k);
   rc |= upload(c, M.lo_k, &d.lo_k);
@@ -413,7 +413,8 @@ extern "C" int moip_verify_int64(moip_ctx* c, int B, const int32_t* x, const dou
 int moip_ctx::attach_k1_scratch(moip::LpBatch& b) {
   b.scratch = nullptr; b.scratch_stride = 0; b.scratch_slots = 0;
   if (dm.reg_ok || dm.fast_ok) return MOIP_OK;
-  const size_t stride = k1_scratch_stride(dm);
+  size_t stride = k1_scratch_stride(dm);
+  if (stride == 0 && std::getenv("MOIP_K1_FORCE_STREAMING")) stride = ((size_t)5 * dm.n + (size_t)8 * dm.m + 15) & ~(size_t)15;   // tests
   if (stride == 0) return MOIP_OK;
   const int slots = num_sms * 4;
   if (k1_scratch.ensure(stride * (size_t)slots)) return MOIP_ERR_CUDA;

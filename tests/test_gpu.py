@@ -216,6 +216,30 @@ def test_k1_fixed_iterations_match_port(mb, tmp_path, kind, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("streaming", [False, True])
+def test_k1_generic_kernel_and_streaming_mode(mb, examples, tmp_path, monkeypatch, streaming):
+    """The generic kernel (models outside the specialised paths) and its streaming mode (iterate in an HBM scratch
+    region, used when 5n + 8m doubles exceed shared memory) give the port's iterates and the golden front."""
+    from oracle import pdhg_oracle as po
+    from oracle.lpformat import write_lp
+    monkeypatch.setenv("MOIP_K1_GENERIC", "1")
+    if streaming:
+        monkeypatch.setenv("MOIP_K1_FORCE_STREAMING", "1")
+    model = _lp_case("ap8")
+    path = str(tmp_path / "ap8.lp")
+    write_lp(model, path)
+    ctx = mb.Context(mb.Problem(path))
+    cost, rhs, masks = po.sample_node_batch(model, 12, seed=3)
+    got = ctx.lp_batch_solve(cost, rhs, masks, mb.Context.lp_params(fixed_iters=40), want_x=True)
+    port = po.pdhg_ref(model, cost, rhs, masks, fixed_iters=40, norm_every=int(os.environ.get("MOIP_NORM_EVERY", "16")))
+    assert np.allclose(got["x"], port["x"], rtol=0, atol=1e-9)
+    ctx.close()
+    e = examples["3AP05"]
+    ctx = mb.Context(mb.Problem(e["path"]))
+    assert ctx.pareto_front() == e["rows"]
+    ctx.close()
+
+
 def test_k1_cutoff_and_edge_cases(mb, examples):
     pr = mb.Problem(examples["2AP05"]["path"])
     ctx = mb.Context(pr)
