@@ -30,8 +30,6 @@ def build(force=False, verbose=False):
                "-Xcompiler", "-fPIC", "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        if os.environ.get("MOIP_K1_EXPERIMENT"):
-            cmd.insert(1, "-DMOIP_K1_EXPERIMENT")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     failed = False

@@ -478,13 +478,9 @@ int launch_fast(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, c
   return MOIP_OK;
 }
 
-#ifdef MOIP_K1_EXPERIMENT
-#define MOIP_KD_CASES(NT, E, MB) case 3: return launch_fast<NT, 3, E, MB>(dm, b, p, num_sms, st); case 5: return launch_fast<NT, 5, E, MB>(dm, b, p, num_sms, st);
-#else
 #define MOIP_KD_CASES(NT, E, MB) case 1: return launch_fast<NT, 1, E, MB>(dm, b, p, num_sms, st); case 2: return launch_fast<NT, 2, E, MB>(dm, b, p, num_sms, st); \
   case 3: return launch_fast<NT, 3, E, MB>(dm, b, p, num_sms, st); case 4: return launch_fast<NT, 4, E, MB>(dm, b, p, num_sms, st); \
   case 5: return launch_fast<NT, 5, E, MB>(dm, b, p, num_sms, st); case 6: return launch_fast<NT, 6, E, MB>(dm, b, p, num_sms, st);
-#endif
 
 template <int NT, int ELLW, int MINB>
 int launch_kd(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
@@ -496,9 +492,7 @@ template <int NT, int MINB>
 int launch_ell(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   switch (dm.ell2_w) {
     case 0: return launch_kd<NT, 0, MINB>(dm, b, p, num_sms, st);
-#ifndef MOIP_K1_EXPERIMENT
     case 1: return launch_kd<NT, 1, MINB>(dm, b, p, num_sms, st);
-#endif
     case 2: return launch_kd<NT, 2, MINB>(dm, b, p, num_sms, st);
   }
   return MOIP_ERR_UNSUPPORTED;
@@ -510,14 +504,6 @@ int launch_k1_fast(const DevModel& dm, const LpBatch& b, const LpParams& p, int 
   if (b.B <= 0) return MOIP_OK;
   MOIP_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(int), st));
   if (dm.n <= 64 && dm.m <= 32) return launch_ell<32, 16>(dm, b, p, num_sms, st);
-#ifdef MOIP_K1_EXPERIMENT
-  switch (env_int("MOIP_K1_CFG", 0)) {
-    case 1: return launch_ell<128, 5>(dm, b, p, num_sms, st);
-    case 2: return launch_ell<128, 6>(dm, b, p, num_sms, st);
-    case 3: return launch_ell<256, 2>(dm, b, p, num_sms, st);
-    case 4: return launch_ell<256, 3>(dm, b, p, num_sms, st);
-  }
-#endif
   return launch_ell<128, 4>(dm, b, p, num_sms, st);     // m <= 128 guaranteed by Model::fast_ok
 }
 

@@ -167,39 +167,6 @@ __global__ void __launch_bounds__(128) k2_branch_kernel(const DevModel dm, const
   }
 }
 
-// gathers the node bounds / warm starts of a batch into contiguous staging (K1 reads [B][n])
-__global__ void __launch_bounds__(128) k2_gather_kernel(const DevModel dm, const PoolView pool, int B, const int* ids,
-                                                        int* lb, int* ub, double* wx, double* wy) {
-  const int n = dm.n, m = dm.m;
-  for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
-    const int slot = ids[bi];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      lb[(size_t)bi * n + j] = pool.lb[(size_t)slot * n + j];
-      ub[(size_t)bi * n + j] = pool.ub[(size_t)slot * n + j];
-      wx[(size_t)bi * n + j] = pool.wx[(size_t)slot * n + j];
-    }
-    for (int i = threadIdx.x; i < m; i += blockDim.x) wy[(size_t)bi * m + i] = pool.wy[(size_t)slot * m + i];
-  }
-}
-
-// after K1: scatter the LP iterate back as the node's warm start and round it to the nearest
-// integer point inside the node's bounds (candidate for K4)
-__global__ void __launch_bounds__(128) k2_scatter_round_kernel(const DevModel dm, const PoolView pool, int B,
-                                                               const int* ids, const double* x, const double* y,
-                                                               int* xr) {
-  const int n = dm.n, m = dm.m;
-  for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
-    const int slot = ids[bi];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const double v = x[(size_t)bi * n + j];
-      pool.wx[(size_t)slot * n + j] = v;
-      int r = (int)llrint(v);
-      r = max(pool.lb[(size_t)slot * n + j], min(pool.ub[(size_t)slot * n + j], r));
-      xr[(size_t)bi * n + j] = r;
-    }
-    for (int i = threadIdx.x; i < m; i += blockDim.x) pool.wy[(size_t)slot * m + i] = y[(size_t)bi * m + i];
-  }
-}
 
 }  // namespace
 
@@ -224,24 +191,6 @@ int launch_k2_branch(const DevModel& dm, const PoolView& pool, int C, const Bran
   if (C <= 0) return MOIP_OK;
   int grid = C < 148 * 8 ? C : 148 * 8;
   k2_branch_kernel<<<grid, 128, 0, st>>>(dm, pool, C, ops);
-  MOIP_CUDA(cudaGetLastError());
-  return MOIP_OK;
-}
-
-int launch_k2_gather(const DevModel& dm, const PoolView& pool, int B, const int* ids, int* lb, int* ub, double* wx,
-                     double* wy, cudaStream_t st) {
-  if (B <= 0) return MOIP_OK;
-  int grid = B < 148 * 8 ? B : 148 * 8;
-  k2_gather_kernel<<<grid, 128, 0, st>>>(dm, pool, B, ids, lb, ub, wx, wy);
-  MOIP_CUDA(cudaGetLastError());
-  return MOIP_OK;
-}
-
-int launch_k2_scatter_round(const DevModel& dm, const PoolView& pool, int B, const int* ids, const double* x,
-                            const double* y, int* xr, cudaStream_t st) {
-  if (B <= 0) return MOIP_OK;
-  int grid = B < 148 * 8 ? B : 148 * 8;
-  k2_scatter_round_kernel<<<grid, 128, 0, st>>>(dm, pool, B, ids, x, y, xr);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }

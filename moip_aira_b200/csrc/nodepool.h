@@ -20,9 +20,5 @@ struct BranchOp {           // child = copy of parent with up to 3 columns tight
 int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const int* ids, const long long* obj_lo,
                         const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st);
 int launch_k2_branch(const DevModel& dm, const PoolView& pool, int C, const BranchOp* ops, cudaStream_t st);
-int launch_k2_gather(const DevModel& dm, const PoolView& pool, int B, const int* ids, int* lb, int* ub, double* wx,
-                     double* wy, cudaStream_t st);
-int launch_k2_scatter_round(const DevModel& dm, const PoolView& pool, int B, const int* ids, const double* x,
-                            const double* y, int* xr, cudaStream_t st);
 
 }  // namespace moip

@@ -140,11 +140,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   c->q_ip.release(); c->q_out.release(); c->q_which.release(); c->h_q.release();
   c->v_x.release(); c->v_rhs.release(); c->v_obj.release(); c->v_feas.release();
   c->p_lb.release(); c->p_ub.release(); c->p_wx.release(); c->p_wy.release();
-  c->r_ids.release(); c->r_flag.release(); c->r_lb.release(); c->r_ub.release(); c->r_status.release();
-  c->r_iters.release(); c->r_branch.release(); c->r_xr.release(); c->r_counter.release();
-  c->r_wx.release(); c->r_wy.release(); c->r_x.release(); c->r_y.release(); c->r_pobj.release();
-  c->r_dbound.release(); c->r_bval.release(); c->r_rhs.release(); c->r_cutoff.release();
-  c->r_leaf.release(); c->r_olo.release(); c->r_ohi.release(); c->r_cobj.release(); c->r_cfeas.release();
+  c->r_xr.release(); c->r_counter.release(); c->r_pobj.release();
   c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release(); c->d_inc.release(); c->d_root_x.release(); c->d_root_y.release(); c->k1_scratch.release();
   delete c;
 }

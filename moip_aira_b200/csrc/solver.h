@@ -99,10 +99,8 @@ struct moip_ctx {
   moip::DBuf<int> p_lb, p_ub;
   moip::DBuf<double> p_wx, p_wy;
   std::vector<int> free_slots;
-  moip::DBuf<int> r_ids, r_flag, r_lb, r_ub, r_status, r_iters, r_branch, r_xr, r_counter;
-  moip::DBuf<double> r_wx, r_wy, r_x, r_y, r_pobj, r_dbound, r_bval, r_rhs, r_cutoff;
-  moip::DBuf<long long> r_leaf, r_olo, r_ohi, r_cobj;
-  moip::DBuf<unsigned char> r_cfeas;
+  moip::DBuf<int> r_xr, r_counter;      // rounded candidates [B][3][n]; K1 work counter
+  moip::DBuf<double> r_pobj;
   moip::DBuf<moip::BranchOp> r_ops;
   moip::HBuf<unsigned char> h_round;    // packed D2H results of one round
   moip::DBuf<unsigned char> r_in, r_out; // one H2D block in / one D2H block out per round (solve_ip)
