@@ -134,7 +134,7 @@ def main():
     ap.add_argument("--workload", default="ap30", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-fronts", action="store_true")
-    ap.add_argument("--front-instance", default="ap3_20_1", help="synthetic instance of tests/golden/synthetic.json whose "
+    ap.add_argument("--front-instance", default="ap3_30_1", help="synthetic instance of tests/golden/synthetic.json whose "
                     "Pareto front is timed with the EPP strips sharded over the ranks (ap3_12_1, ap3_15_1, ap3_20_1, kp4_25_1 ...)")
     ap.add_argument("--front-strips-per-gpu", type=int, default=12)
     args = ap.parse_args()
@@ -296,6 +296,8 @@ def main():
             line.setdefault("time_to_front_s", {})[f"{args.front_instance} --split -t {args.front_strips_per_gpu * world}"] = fr
     if print_line:
         print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
     return 0
 
 
