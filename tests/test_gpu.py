@@ -383,7 +383,7 @@ def test_front_synthetic_golden_sequential(mb, tmp_path, name):
 
 
 @pytest.mark.parametrize("name,strips,workers", [("ap3_12_1", 12, 12), ("ap3_15_1", 12, 12), ("kp4_25_1", 8, 8), ("kp3_40_1", 12, 6),
-                                                 ("ap3_20_1", 12, 12), ("ap3_30_1", 12, 12)])
+                                                 ("ap3_20_1", 12, 12), ("ap3_30_1", 12, 12), ("kp4_40_1", 12, 12)])
 def test_front_synthetic_golden_pool(mb, tmp_path, name, strips, workers):
     """Same, larger instances, EPP strips solved concurrently on one GPU (--split -t strips)."""
     path, want = _synthetic_case(name, tmp_path)
