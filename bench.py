@@ -263,7 +263,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k1_reg_kernel<256,4,3,2,2>",
+                         "traffic": None, "peak_kind": peak_kind,
+                         "kernel": "k1_reg_kernel<256,4,3,2,2>" if args.workload == "ap30" else "k1_small_kernel<5,5,3>",
                          "algorithmic_bytes_per_node_iter": bytes_iter,
                          "node_iters_per_launch": my_iters / args.steps,
                          "note": "iterates stay in shared memory across iterations; HBM traffic is far below the "
@@ -276,7 +277,7 @@ def main():
                    "fixed_1000_iterations": {"ms": fixed_ms, "node_iters_per_sec": B * 1000 / (fixed_ms * 1e-3),
                                              "roofline_frac": B * 1000 * bytes_iter / (fixed_ms * 1e-3) / 1e9 / peak}}}
     tr = os.path.join(ROOT, "profiles", "k1_traffic.json")      # dram bytes per launch of this command from ncu --set full
-    if rank == 0 and os.path.exists(tr):
+    if rank == 0 and os.path.exists(tr) and args.workload == "ap30" and B == 16384:
         line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
     if world == 1:
