@@ -186,6 +186,11 @@ int moip_pool_get_limit(moip_pool* p, int obj, int sense, const double* rhs, int
  * the workers; rows_out receives the feasible result vectors (k ints per row, unsorted) */
 int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const double* start_stop, int* rows_out, int cap,
                          int* n_rows);
+/* same with a caller-supplied strip dispenser (returns the next strip index, anything outside [0, nstrips) ends the
+ * calling worker): one global counter can feed the pools of several GPUs / ranks */
+typedef int (*moip_claim_fn)(void* user);
+int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, const double* start_stop, moip_claim_fn claim,
+                               void* user, int* rows_out, int cap, int* n_rows);
 /* main() with --split -t num_threads (src/aira.cpp:269-276, :1945-1990): every level's strips run
  * concurrently on the pool; rows_out = sorted, de-duplicated front */
 int moip_pool_pareto_front(moip_pool* p, int num_threads, int split_normal, int* rows_out, int cap, int* n_rows);

@@ -59,6 +59,7 @@ SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINT
                        C.POINTER(C.c_int), C.POINTER(C.c_int))
 FIND_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int))
 INSERT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int)
+CLAIM_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 _pi, _pd = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -100,6 +101,7 @@ _SIGS = {
     "moip_pool_stats": (_i, [_vp, C.POINTER(Stats)]),
     "moip_pool_get_limit": (_i, [_vp, _i, _i, _pd, _pi, _pi]),
     "moip_pool_run_strips": (_i, [_vp, _i, _i, _pd, _pi, _i, _pi]),
+    "moip_pool_run_strips_claim": (_i, [_vp, _i, _i, _pd, CLAIM_FN, _vp, _pi, _i, _pi]),
     "moip_pool_pareto_front": (_i, [_vp, _i, _i, _pi, _i, _pi]),
     "moip_version": (C.c_char_p, []),
 }
@@ -324,15 +326,22 @@ class WorkerPool:
                                         C.byref(st)), "pool_get_limit")
         return st.value, ([int(v) for v in res] if st.value != MIP_INFEASIBLE else None)
 
-    def run_strips(self, n_obj, strips, cap=1 << 14):
-        """strips: list of (start, stop); returns the feasible result rows found (unsorted)."""
+    def run_strips(self, n_obj, strips, claim=None, cap=1 << 16):
+        """strips: list of (start, stop); returns the feasible result rows found (unsorted).  `claim`: optional
+        callable returning the index of the next strip to solve (shared by the pools of several ranks); without it
+        the pool works through all the strips given."""
         k = self.problem.objcnt
         ss = np.ascontiguousarray(np.asarray(strips, dtype=np.float64).reshape(-1, 2))
         rows = np.zeros((cap, k), dtype=np.int32)
         n = C.c_int(0)
-        _check(_lib.moip_pool_run_strips(self._h, int(n_obj), len(ss), _dp(ss), _ip(rows), cap, C.byref(n)), "pool_run_strips")
+        if claim is None:
+            _check(_lib.moip_pool_run_strips(self._h, int(n_obj), len(ss), _dp(ss), _ip(rows), cap, C.byref(n)), "pool_run_strips")
+        else:
+            cb = CLAIM_FN(lambda _user: int(claim()))
+            _check(_lib.moip_pool_run_strips_claim(self._h, int(n_obj), len(ss), _dp(ss), cb, None, _ip(rows), cap, C.byref(n)),
+                   "pool_run_strips_claim")
         if n.value > cap:
-            return self.run_strips(n_obj, strips, cap=n.value)
+            raise MoipError("more result rows than the buffer holds")
         return [tuple(int(v) for v in r) for r in rows[:n.value]]
 
     def pareto_front(self, num_threads=8, split_normal=False, cap=1 << 16):

@@ -63,6 +63,24 @@ class Dist:
         if self.world > 1:
             self.pg.barrier()
 
+    def counter(self, name):
+        """Job-wide atomic counter (0, 1, 2, ...): the ranks draw EPP strips from it, so that no GPU idles while
+        another still has strips queued.  One process: a local counter; several: the job's c10d store."""
+        if self.world == 1:
+            import itertools
+            import threading
+            it, lock = itertools.count(), threading.Lock()
+
+            def nxt():
+                with lock:
+                    return next(it)
+            return nxt
+        from torch.distributed import distributed_c10d
+        store = distributed_c10d._get_default_store()
+        self._seq = getattr(self, "_seq", 0) + 1          # every rank makes the same sequence of calls
+        key = "moip_strips_%d_%s" % (self._seq, name)
+        return lambda: store.add(key, 1) - 1
+
 
 # ------------------------------------------------------------------------------------ backends
 class GpuBackend:
@@ -96,10 +114,10 @@ class GpuBackend:
         st, res = self.pool.get_limit(obj, rhs)
         return res
 
-    def run_strips(self, n_obj, strips):
-        """The strips this rank owns at one EPP level, solved concurrently and sharing `here`/`infeasibles`
-        like the reference's threads."""
-        return self.pool.run_strips(n_obj, [s for _, s in strips])
+    def run_strips(self, n_obj, strips, claim):
+        """The strips of one EPP level: this rank's workers draw strip indices from `claim` (shared by all ranks),
+        solve them concurrently and share `here`/`infeasibles` like the reference's threads."""
+        return self.pool.run_strips(n_obj, strips, claim)
 
     def sequential_front(self):
         return self.ctx.pareto_front()
@@ -141,8 +159,7 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):
             if biggest == smallest:
                 smallest = INT_MIN
         strips = be.split_strips(biggest, smallest, num_threads, split_normal)
-        mine = [(t, s) for t, s in enumerate(strips) if t % dist.world == dist.rank]
-        rows = be.run_strips(n_obj, mine) if mine else []
+        rows = be.run_strips(n_obj, strips, dist.counter("level%d" % n_obj))
         return dist.allgather_rows(rows, k)
 
     rows = level(k)

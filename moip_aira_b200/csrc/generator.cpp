@@ -343,6 +343,14 @@ extern "C" int moip_pool_get_limit(moip_pool* p, int obj, int sense, const doubl
 // pairs; rows_out receives the feasible result vectors found (k ints per row, unsorted, duplicates possible)
 extern "C" int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const double* start_stop, int* rows_out, int cap,
                                     int* n_rows) {
+  return moip_pool_run_strips_claim(p, n_obj, nstrips, start_stop, nullptr, nullptr, rows_out, cap, n_rows);
+}
+
+// Same, but every worker asks `claim` for the index of its next strip (values >= nstrips end the worker): lets
+// several pools -- one per GPU / rank -- draw from one global counter, so that no rank idles while another still
+// has strips queued.  claim == nullptr: local counter.
+extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, const double* start_stop, moip_claim_fn claim,
+                                          void* user, int* rows_out, int cap, int* n_rows) {
   if (!p || p->ctx.empty() || nstrips < 0 || (nstrips > 0 && !start_stop) || !n_rows) return MOIP_ERR_ARG;
   const int k = p->ctx[0]->dm.k;
   if (n_obj < 1 || n_obj > k) return MOIP_ERR_ARG;
@@ -367,8 +375,8 @@ extern "C" int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const 
       if (!rc) rc = moip_cache_create(c, &infeasibles);
     }
     while (!rc && !failed.load()) {
-      const int t = next.fetch_add(1);
-      if (t >= nstrips) break;
+      const int t = claim ? claim(user) : next.fetch_add(1);
+      if (t < 0 || t >= nstrips) break;
       moip_worker w{};
       w.id = t; w.n_obj = n_obj; w.split = 1;
       for (int i = 0; i < k; ++i) w.perm[i] = i;                            // thread.cpp:124-133

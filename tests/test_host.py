@@ -138,7 +138,7 @@ class _OracleBackend:
     def get_limit(self, obj, rhs):
         return self.fs.get_limit(obj, rhs)
 
-    def run_strips(self, n_obj, strips):
+    def run_strips(self, n_obj, strips, claim):
         here, inf = ao.Solutions(self.k), ao.Solutions(self.k)
 
         def find(ip):
@@ -150,7 +150,11 @@ class _OracleBackend:
         def insert(ip, res, infeasible):
             (inf if infeasible else here).insert(ip, res, infeasible)
 
-        for t, (a, b) in strips:
+        while True:
+            t = claim()                       # job-wide counter: every strip is solved by exactly one rank
+            if t >= len(strips):
+                break
+            a, b = strips[t]
             w = self.mb.make_worker(self.k, n_obj=n_obj, split=True, split_start=a, split_stop=b, wid=t)
             self.mb.optimise_with(self.k, self.sense, w, self.fs.lex_solve, find, insert)
         return [tuple(r.result) for r in here.store if not r.infeasible]
