@@ -130,7 +130,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--workload", default="ap30", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=256)
     ap.add_argument("--no-fronts", action="store_true")
@@ -277,7 +277,7 @@ def main():
                    "fixed_1000_iterations": {"ms": fixed_ms, "node_iters_per_sec": B * 1000 / (fixed_ms * 1e-3),
                                              "roofline_frac": B * 1000 * bytes_iter / (fixed_ms * 1e-3) / 1e9 / peak}}}
     tr = os.path.join(ROOT, "profiles", "k1_traffic.json")      # dram bytes per launch of this command from ncu --set full
-    if rank == 0 and os.path.exists(tr) and args.workload == "ap30" and B == 16384:
+    if rank == 0 and os.path.exists(tr) and args.workload == "ap30" and B == 65536:
         line["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
     if world == 1:
