@@ -69,6 +69,11 @@ int moip_model_objcoef(const moip_model* m, int obj, double* out_n);
 int moip_model_dense(const moip_model* m, double* a_ms_n, char* row_sense_ms, double* rhs_ms,
                      double* lb_n, double* ub_n, uint8_t* is_int_n);
 int moip_model_colname(const moip_model* m, int j, char* buf, int buflen); /* CPXgetcolname, src/problem.cpp:183 */
+/* Which K1 kernel the model maps to and whether the packed device images are consistent with the model (every
+ * nonzero present exactly once, shared-memory offsets in range and collision free, scalings reproduce the matrix).
+ * No device needed.  kernel_path: 0 generic, 1 k1_fast, 2 k1_reg, 3 k1_small, 4 generic in streaming mode.
+ * Returns MOIP_OK, or MOIP_ERR_LIMIT with a description in msg when an invariant is violated. */
+int moip_model_selfcheck(const moip_model* m, int* kernel_path, char* msg, int msglen);
 
 /* ---- context: one per worker (src/aira.cpp:561-585). `stream` is a cudaStream_t (NULL = default). */
 int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx** out);

@@ -70,6 +70,7 @@ _SIGS = {
     "moip_model_objcoef": (_i, [_vp, _i, _pd]),
     "moip_model_dense": (_i, [_vp, _pd, C.c_char_p, _pd, _pd, _pd, C.POINTER(C.c_uint8)]),
     "moip_model_colname": (_i, [_vp, _i, C.c_char_p, _i]),
+    "moip_model_selfcheck": (_i, [_vp, _pi, C.c_char_p, _i]),
     "moip_ctx_create": (_i, [_vp, _i, _vp, C.POINTER(_vp)]),
     "moip_ctx_destroy": (None, [_vp]),
     "moip_lp_default_params": (None, [C.POINTER(LpParams)]),
@@ -154,6 +155,15 @@ class Problem:
         _check(_lib.moip_model_dense(self._h, _dp(A), sense, _dp(b), _dp(lb), _dp(ub),
                                      isint.ctypes.data_as(C.POINTER(C.c_uint8))), "dense")
         return A, [chr(c) for c in sense.raw[:ms]], b[:ms], lb, ub, isint.astype(bool)
+
+    KERNEL_PATHS = {0: "generic", 1: "k1_fast", 2: "k1_reg", 3: "k1_small", 4: "generic-streaming"}
+
+    def selfcheck(self):
+        """(kernel path name, error text or None): consistency of the packed device images, no GPU needed"""
+        path = C.c_int(-1)
+        buf = C.create_string_buffer(256)
+        rc = _lib.moip_model_selfcheck(self._h, C.byref(path), buf, 256)
+        return self.KERNEL_PATHS.get(path.value, "?"), (None if rc == 0 else buf.value.decode())
 
     def colnames(self):
         buf = C.create_string_buffer(1024)

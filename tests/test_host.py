@@ -53,6 +53,29 @@ def test_loader_matches_oracle_reader(lib, examples, stem):
     assert np.all(np.abs(pr.rhs) == 1e20)                    # src/problem.cpp:122-132
 
 
+@pytest.mark.parametrize("kind,k,n,path", [("ap", 3, 30, "k1_reg"), ("ap", 3, 12, "k1_reg"), ("ap", 4, 16, "k1_reg"), ("ap", 2, 20, "k1_reg"),
+                                           ("ap", 3, 5, "k1_fast"), ("ap", 2, 40, "k1_fast"), ("ap", 2, 72, "generic-streaming"),
+                                           ("kp", 4, 40, "k1_small"), ("kp", 3, 10, "k1_small"), ("kp", 2, 50, "k1_small"),
+                                           ("kp", 3, 100, "k1_reg"), ("kp", 2, 2000, "k1_fast")])
+def test_packed_kernel_images_are_consistent(lib, tmp_path, kind, k, n, path):
+    """Host half of K1 (no GPU): the packed column records reproduce the scaled matrix, every short-row nonzero owns
+    exactly one in-range product slot of the register-resident kernel, and the model maps to the expected kernel."""
+    from moip_aira_b200 import instances
+    p = str(tmp_path / f"{kind}{k}_{n}.lp")
+    (instances.write_ap if kind == "ap" else instances.write_kp)(p, n, k, 1)
+    got, err = lib.Problem(p).selfcheck()
+    assert err is None, err
+    assert got == path
+
+
+def test_packed_kernel_images_of_the_examples(lib, examples):
+    want = {"2AP05": "k1_fast", "3AP05": "k1_fast", "4AP05": "k1_fast", "3KP10": "k1_small", "4KP10": "k1_small",
+            "2KP50": "k1_small", "moip_2_30_1_knapsack": "k1_small"}
+    for stem, path in want.items():
+        got, err = lib.Problem(examples[stem]["path"]).selfcheck()
+        assert err is None and got == path, (stem, got, err)
+
+
 def test_loader_rejects_bad_input(lib, tmp_path):
     p = tmp_path / "bad.lp"
     p.write_text("Minimize 0\nsubject to\n x + y <= 3\n x + 2 y < 7\nBINARY\n x\n y\nEND\n")   # k = 7 > rows
