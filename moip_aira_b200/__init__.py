@@ -336,7 +336,7 @@ class WorkerPool:
                                         C.byref(st)), "pool_get_limit")
         return st.value, ([int(v) for v in res] if st.value != MIP_INFEASIBLE else None)
 
-    def run_strips(self, n_obj, strips, claim=None, cap=1 << 16):
+    def run_strips(self, n_obj, strips, claim=None, cap=1 << 20):
         """strips: list of (start, stop); returns the feasible result rows found (unsorted).  `claim`: optional
         callable returning the index of the next strip to solve (shared by the pools of several ranks); without it
         the pool works through all the strips given."""
