@@ -134,6 +134,13 @@ int moip_lex_solve(moip_ctx* c, const int* perm, int n_obj, const double* rhs, i
  * result is left untouched when infeasible, like the reference (:410-412). */
 int moip_get_limit(moip_ctx* c, int obj, int sense, const double* rhs, int* result, int* mip_status);
 
+/* Seam 1 primitive: one CPXmipopt + CPXgetstat + CPXgetobjval + CPXgetx (src/aira.cpp:480-521): optimise objective
+ * `obj` in the model's sense under the k objective-bound rows at `rhs`; x_out[n] and *objval are written unless the
+ * problem is infeasible.  x_start (or NULL) is a point known to satisfy the model and `rhs` (MIP start).  Used by the
+ * link-level CPLEX shim in moip_aira_b200/seam1/, which lets the unmodified reference sources run on this library. */
+int moip_mip_solve(moip_ctx* c, int obj, const double* rhs, const int32_t* x_start, int32_t* x_out,
+                   int64_t* objval, int* mip_status);
+
 /* counters (ipcount of src/aira.cpp:80 and the FINETIMING split of :554-560) */
 typedef struct {
   int64_t ip_solved;      /* single-objective IPs solved (CPXmipopt calls in the reference) */

@@ -89,6 +89,7 @@ _SIGS = {
     "moip_verify_int64": (_i, [_vp, _i, _pi, _pd, C.POINTER(C.c_int64), C.POINTER(C.c_uint8)]),
     "moip_lex_solve": (_i, [_vp, _pi, _i, _pd, _pi, _pi]),
     "moip_get_limit": (_i, [_vp, _i, _i, _pd, _pi, _pi]),
+    "moip_mip_solve": (_i, [_vp, _i, _pd, _pi, _pi, C.POINTER(C.c_int64), _pi]),
     "moip_ctx_stats": (_i, [_vp, C.POINTER(Stats)]),
     "moip_ctx_reset_stats": (_i, [_vp]),
     "moip_optimise": (_i, [_vp, C.POINTER(Worker), _vp, _vp]),

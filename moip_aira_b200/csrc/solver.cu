@@ -813,6 +813,26 @@ int moip_ctx::get_limit(int obj, int sense, const double* rhs, int* result, int*
   return MOIP_OK;
 }
 
+// One CPXmipopt (+ CPXgetstat / CPXgetobjval / CPXgetx): optimise objective `obj` in the model's sense subject to the
+// structural rows and the k objective-bound rows at `rhs`.  x_start, when given, must satisfy all of them.
+extern "C" int moip_mip_solve(moip_ctx* c, int obj, const double* rhs, const int32_t* x_start, int32_t* x_out,
+                              int64_t* objval, int* mip_status) {
+  if (!c || !rhs || obj < 0 || obj >= c->dm.k) return MOIP_ERR_ARG;
+  const double t0 = now_s();
+  std::vector<int> start;
+  if (x_start) start.assign(x_start, x_start + c->dm.n);
+  IpResult r;
+  int rc = c->solve_ip(obj, rhs, x_start ? &start : nullptr, r);
+  if (rc) return rc;
+  if (mip_status) *mip_status = r.status;
+  if (r.status != MOIP_MIP_INFEASIBLE) {
+    if (x_out) for (int j = 0; j < c->dm.n; ++j) x_out[j] = r.x[j];
+    if (objval) *objval = r.obj;
+  }
+  c->stats.solver_seconds += now_s() - t0;
+  return MOIP_OK;
+}
+
 extern "C" int moip_lex_solve(moip_ctx* c, const int* perm, int n_obj, const double* rhs, int* result, int* mip_status) {
   if (!c || !perm || !rhs || !result || n_obj < 1 || n_obj > c->dm.k) return MOIP_ERR_ARG;
   for (int i = 0; i < c->dm.k; ++i) if (perm[i] < 0 || perm[i] >= c->dm.k) return MOIP_ERR_ARG;
