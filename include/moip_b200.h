@@ -77,7 +77,12 @@ int moip_model_selfcheck(const moip_model* m, int* kernel_path, char* msg, int m
 
 /* ---- context: one per worker (src/aira.cpp:561-585). `stream` is a cudaStream_t (NULL = default). */
 int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx** out);
+/* same on a non-blocking stream created and owned by the context (callers that hold no CUDA handles: the
+ * link-level CPLEX seam creates one context per CPXLPptr, src/aira.cpp:561-585) */
+int moip_ctx_create_own_stream(moip_model* m, int device, moip_ctx** out);
 void moip_ctx_destroy(moip_ctx* c);
+/* number of usable CUDA devices (0 when there is none); lets a threaded host place one worker per GPU */
+int moip_device_count(void);
 
 /* ---- K1: batched node-LP relaxations (inside CPXmipopt today, src/aira.cpp:480) ------------- */
 typedef struct {

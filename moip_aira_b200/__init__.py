@@ -72,6 +72,8 @@ _SIGS = {
     "moip_model_colname": (_i, [_vp, _i, C.c_char_p, _i]),
     "moip_model_selfcheck": (_i, [_vp, _pi, C.c_char_p, _i]),
     "moip_ctx_create": (_i, [_vp, _i, _vp, C.POINTER(_vp)]),
+    "moip_ctx_create_own_stream": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "moip_device_count": (_i, []),
     "moip_ctx_destroy": (None, [_vp]),
     "moip_lp_default_params": (None, [C.POINTER(LpParams)]),
     "moip_lp_batch_solve": (_i, [_vp, _i, _pi, _pd, C.POINTER(C.c_uint32), C.POINTER(LpParams), _pd, _pd, _pi, _pi, _pd]),

@@ -45,5 +45,23 @@ def build(force=False, verbose=False):
     return LIB
 
 
+SEAM1 = os.path.join(HERE, "seam1")
+SEAM1_LIB = os.path.join(SEAM1, "libcplex_moip_b200.so")
+
+
+def build_seam1(force=False):
+    """Link-level CPLEX seam (Seam 1): seam1/cpx_shim.cpp -> seam1/libcplex_moip_b200.so, host code only
+    (g++), linked against libmoip_b200.so next to it."""
+    src = os.path.join(SEAM1, "cpx_shim.cpp")
+    deps = [src, os.path.join(SEAM1, "include", "ilcplex", "cplex.h"), os.path.join(HERE, "..", "include", "moip_b200.h"), LIB]
+    if not force and os.path.exists(SEAM1_LIB) and all(os.path.getmtime(d) <= os.path.getmtime(SEAM1_LIB) for d in deps):
+        return SEAM1_LIB
+    cxx = os.environ.get("CXX", "g++")
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", src, "-o", SEAM1_LIB,
+                           "-L" + HERE, "-lmoip_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return SEAM1_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_seam1(force="--force" in sys.argv))

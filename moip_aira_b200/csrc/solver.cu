@@ -142,7 +142,35 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   c->p_lb.release(); c->p_ub.release(); c->p_wx.release(); c->p_wy.release();
   c->r_xr.release(); c->r_counter.release(); c->r_pobj.release();
   c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release(); c->d_inc.release(); c->d_root_x.release(); c->d_root_y.release(); c->k1_scratch.release();
+  if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+// Context on a non-blocking stream of its own: what a worker thread that holds no CUDA handles needs (the link-level
+// CPLEX seam: one context per CPXLPptr, reference src/aira.cpp:561-585).
+extern "C" int moip_ctx_create_own_stream(moip_model* m, int device, moip_ctx** out) {
+  if (!m || !out) return MOIP_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    std::fprintf(stderr, "moip_b200: no CUDA device available (this library has no CPU fallback)\n");
+    return MOIP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) return MOIP_ERR_ARG;
+  cudaStream_t st = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
+    std::fprintf(stderr, "moip_b200: cannot create a stream on device %d\n", device);
+    return MOIP_ERR_CUDA;
+  }
+  int rc = moip_ctx_create(m, device, st, out);
+  if (rc) { cudaStreamDestroy(st); return rc; }
+  (*out)->owns_stream = true;
+  return MOIP_OK;
+}
+
+extern "C" int moip_device_count(void) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) return 0;
+  return ndev;
 }
 
 extern "C" int moip_ctx_stats(const moip_ctx* c, moip_stats* out) {

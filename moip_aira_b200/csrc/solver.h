@@ -77,6 +77,7 @@ struct moip_ctx {
   moip_model* model = nullptr;
   int device = 0;
   cudaStream_t stream = 0;
+  bool owns_stream = false;   // moip_ctx_create_own_stream: destroyed with the context
   int num_sms = 148;
   moip::DevModel dm{};
   std::vector<void*> model_allocs;

@@ -1,0 +1,269 @@
+"""Link-level drop-in seam ("Seam 1"): the 23 CPX* entry points the reference binds, served by
+libcplex_moip_b200.so, and the UNMODIFIED reference driver built on them (oracle/_ref/aira_seam1, recipe in
+oracle/Makefile) run through the reference's own CTest matrix (Examples/CMakeLists.txt: 6 .lp instances x
+{default, -t 2, -t 2 -s, -t 2 --split, -t 2 --split --split-normal}, compared by scripts/checkResults.sh's rule).
+
+CPU tests (`-m "not gpu"`): the shim's model-side calls answer what Problem::read_lp_problem / read_mop_problem
+expect, unsupported requests and a missing GPU fail loudly, and the reference driver reproduces the golden fronts
+when the three solver entry points are served by the LD_PRELOAD test double oracle/fake_mip_backend.cpp
+(enumeration; test infrastructure).  GPU tests (`-m gpu`): the same matrix with no preload -- every CPXmipopt is
+the GPU branch and bound -- plus 2KP50 and the .mop instance, and a check that kernels were launched."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SEAM_LIB = os.path.join(ROOT, "moip_aira_b200", "seam1", "libcplex_moip_b200.so")
+SEAM_HEADER = os.path.join(ROOT, "moip_aira_b200", "seam1", "include", "ilcplex", "cplex.h")
+AIRA = os.path.join(ROOT, "oracle", "_ref", "aira_seam1")
+FAKE = os.path.join(ROOT, "oracle", "_build", "libfake_mip.so")
+
+# the reference's CTest matrix (Examples/CMakeLists.txt)
+CTEST_OPTS = {"default": [], "group2": ["-t", "2"], "spread2": ["-t", "2", "-s"], "flat2": ["-t", "2", "--split"],
+              "normal2": ["-t", "2", "--split", "--split-normal"]}
+SMALL = ["2AP05", "3AP05", "4AP05", "3KP10", "4KP10"]
+
+needs_aira = pytest.mark.skipif(not os.path.exists(AIRA), reason="oracle/_ref/aira_seam1 is built from /root/reference "
+                                "(oracle/Makefile) and travels prebuilt; absent here")
+
+
+def comparable(out_text):
+    """scripts/checkResults.sh:10 -- diff -w -I 'seconds|solved|Using': drop those lines, ignore white space."""
+    keep = [" ".join(l.split()) for l in out_text.splitlines() if not re.search(r"seconds|solved|Using", l)]
+    return [l for l in keep]
+
+
+def run_aira(path, out, opts, preload=None, extra_env=None, timeout=600):
+    env = dict(os.environ)
+    if preload:
+        env["LD_PRELOAD"] = preload
+    env.update(extra_env or {})
+    return subprocess.run([AIRA, "-p", path, "-o", out] + opts, env=env, capture_output=True, text=True, timeout=timeout)
+
+
+@pytest.fixture(scope="module")
+def cpx(lib):
+    """ctypes view of the shim, signatures from seam1/include/ilcplex/cplex.h"""
+    L = C.CDLL(SEAM_LIB)
+    vp, i, pi, pd = C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    sig = {
+        "CPXopenCPLEX": (vp, [pi]), "CPXcloseCPLEX": (i, [C.POINTER(vp)]), "CPXcreateprob": (vp, [vp, pi, C.c_char_p]),
+        "CPXfreeprob": (i, [vp, C.POINTER(vp)]), "CPXreadcopyprob": (i, [vp, vp, C.c_char_p, C.c_char_p]),
+        "CPXgetnumcols": (i, [vp, vp]), "CPXgetnumrows": (i, [vp, vp]), "CPXgetnumnz": (i, [vp, vp]),
+        "CPXgetrhs": (i, [vp, vp, pd, i, i]), "CPXgetrows": (i, [vp, vp, pi, pi, pi, pd, i, pi, i, i]),
+        "CPXgetobjsen": (i, [vp, vp]), "CPXchgsense": (i, [vp, vp, i, pi, C.c_char_p]),
+        "CPXchgrhs": (i, [vp, vp, i, pi, pd]),
+        "CPXgetcolname": (i, [vp, vp, C.POINTER(C.c_char_p), C.c_char_p, i, pi, i, i]),
+        "CPXaddrows": (i, [vp, vp, i, i, i, pd, C.c_char_p, pi, pi, pd, vp, vp]), "CPXchgobj": (i, [vp, vp, i, pi, pd]),
+        "CPXchgobjsen": (i, [vp, vp, i]), "CPXsetintparam": (i, [vp, i, i]), "CPXsetdblparam": (i, [vp, i, C.c_double]),
+        "CPXmipopt": (i, [vp, vp]), "CPXgetstat": (i, [vp, vp]), "CPXgetobjval": (i, [vp, vp, pd]),
+        "CPXgetx": (i, [vp, vp, pd, i, i]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    L._names = sorted(sig)
+    return L
+
+
+def test_shim_exports_every_declared_entry_point(cpx):
+    header = re.sub(r"/\*.*?\*/", "", open(SEAM_HEADER).read(), flags=re.S)
+    declared = set(re.findall(r"\b(CPX[A-Za-z]+)\s*\(", header))
+    assert len(declared) == 23, sorted(declared)                      # the complete surface
+    out = subprocess.check_output(["nm", "-D", "--defined-only", SEAM_LIB], text=True)
+    exported = set(re.findall(r"\bT (CPX[A-Za-z]+)", out))
+    assert declared == exported == set(cpx._names)
+    # the seam itself contains no solver: it imports the compute entry points from libmoip_b200
+    undefined = subprocess.check_output(["nm", "-D", "--undefined-only", SEAM_LIB], text=True)
+    assert "moip_mip_solve" in undefined and "moip_ctx_create_own_stream" in undefined
+
+
+def open_problem(cpx, path):
+    st = C.c_int(-1)
+    env = cpx.CPXopenCPLEX(C.byref(st))
+    assert env and st.value == 0
+    lp = cpx.CPXcreateprob(env, C.byref(st), path.encode())
+    assert lp and st.value == 0
+    assert cpx.CPXreadcopyprob(env, lp, path.encode(), None) == 0
+    return C.c_void_p(env), C.c_void_p(lp)
+
+
+def close_problem(cpx, env, lp):
+    assert cpx.CPXfreeprob(env, C.byref(lp)) == 0 and not lp.value
+    assert cpx.CPXcloseCPLEX(C.byref(env)) == 0 and not env.value
+
+
+@pytest.mark.parametrize("stem", SMALL + ["2KP50"])
+def test_shim_answers_what_read_lp_problem_asks(cpx, lib, examples, stem):
+    """The call sequence of Problem::read_lp_problem (src/problem.cpp:28-152) against the shim."""
+    from oracle.lpformat import read_model
+    model = read_model(examples[stem]["path"])
+    env, lp = open_problem(cpx, examples[stem]["path"])
+    n, rows, nz = cpx.CPXgetnumcols(env, lp), cpx.CPXgetnumrows(env, lp), cpx.CPXgetnumnz(env, lp)
+    k = model.k
+    assert n == model.n and rows == model.ms + k
+    rhs = (C.c_double * 1)()
+    assert cpx.CPXgetrhs(env, lp, rhs, rows - 1, rows - 1) == 0 and int(rhs[0]) == k       # :54-61
+    beg, ind, val = (C.c_int * rows)(), (C.c_int * nz)(), (C.c_double * nz)()
+    nzcnt, surplus = C.c_int(), C.c_int()
+    assert cpx.CPXgetrows(env, lp, C.byref(nzcnt), beg, ind, val, nz, C.byref(surplus), rows - k, rows - 1) == 0   # :87
+    assert surplus.value >= 0
+    for j in range(k):
+        lo = beg[j]
+        hi = nzcnt.value if j == k - 1 else beg[j + 1]
+        coef = [0.0] * n
+        for e in range(lo, hi):
+            coef[ind[e]] = val[e]
+        assert coef == [float(v) for v in model.C[j]]
+    assert cpx.CPXgetobjsen(env, lp) == (1 if model.sense == "MIN" else -1)                      # :119
+    conind = (C.c_int * k)(*range(rows - k, rows))
+    sense = (b"L" if model.sense == "MIN" else b"G") * k
+    assert cpx.CPXchgsense(env, lp, k, conind, sense) == 0                                   # :141
+    inf = (C.c_double * k)(*([1e20 if model.sense == "MIN" else -1e20] * k))
+    assert cpx.CPXchgrhs(env, lp, k, conind, inf) == 0                                       # :148
+    # outside the supported family: loud and nonzero, never a silent wrong answer
+    assert cpx.CPXchgsense(env, lp, 1, (C.c_int * 1)(0), b"G" if model.sense == "MIN" else b"L") != 0
+    assert cpx.CPXchgrhs(env, lp, 1, (C.c_int * 1)(0), (C.c_double * 1)(3.0)) != 0
+    assert cpx.CPXgetrhs(env, lp, rhs, rows, rows) != 0
+    assert cpx.CPXsetintparam(env, 1067, 1) == 0 and cpx.CPXsetintparam(env, 4242, 1) != 0
+    assert cpx.CPXsetdblparam(env, 2009, 1e-6) == 0
+    close_problem(cpx, env, lp)
+
+
+def test_shim_answers_what_read_mop_problem_asks(cpx, lib, examples):
+    """Problem::read_mop_problem (src/problem.cpp:157-340): rows = structural rows until CPXaddrows appends the k
+    objective rows; column names drive the reference's own re-parse of the file."""
+    from oracle.lpformat import read_model
+    path = examples["moip_2_30_1_knapsack"]["path"]
+    model = read_model(path)
+    env, lp = open_problem(cpx, path)
+    n, k = model.n, model.k
+    assert cpx.CPXgetnumcols(env, lp) == n and cpx.CPXgetnumrows(env, lp) == model.ms
+    names = (C.c_char_p * n)()
+    store = C.create_string_buffer(n * 1024)
+    surplus = C.c_int()
+    assert cpx.CPXgetcolname(env, lp, names, store, n * 1024, C.byref(surplus), 0, n - 1) == 0 and surplus.value > 0
+    assert [s.decode() for s in names] == list(model.names)
+    assert cpx.CPXgetcolname(env, lp, names, store, 4, C.byref(surplus), 0, n - 1) != 0 and surplus.value < 0
+    # CPXmipopt before the objective rows exist is refused
+    assert cpx.CPXmipopt(env, lp) != 0
+    flat = [float(v) for j in range(k) for v in model.C[j]]
+    beg = (C.c_int * k)(*[j * n for j in range(k)])
+    ind = (C.c_int * (k * n))(*(list(range(n)) * k))
+    val = (C.c_double * (k * n))(*flat)
+    rhs = (C.c_double * k)(*([1e20 if model.sense == "MIN" else -1e20] * k))
+    sense = (b"L" if model.sense == "MIN" else b"G") * k
+    wrong = (C.c_double * (k * n))(*([1.0] + flat[1:]))
+    assert cpx.CPXaddrows(env, lp, 0, k, k * n, rhs, sense, beg, ind, wrong, None, None) != 0
+    assert cpx.CPXaddrows(env, lp, 0, k, k * n, rhs, sense, beg, ind, val, None, None) == 0
+    assert cpx.CPXgetnumrows(env, lp) == model.ms + k
+    assert cpx.CPXaddrows(env, lp, 0, k, k * n, rhs, sense, beg, ind, val, None, None) != 0   # once
+    close_problem(cpx, env, lp)
+
+
+def test_shim_objective_must_be_one_of_the_models(cpx, lib, examples):
+    from oracle.lpformat import read_model
+    path = examples["3KP10"]["path"]
+    model = read_model(path)
+    env, lp = open_problem(cpx, path)
+    n = model.n
+    idx = (C.c_int * n)(*range(n))
+    for j in range(model.k):
+        assert cpx.CPXchgobj(env, lp, n, idx, (C.c_double * n)(*[float(v) for v in model.C[j]])) == 0
+    assert cpx.CPXchgobj(env, lp, n, idx, (C.c_double * n)(*([1.0] * n))) != 0
+    assert cpx.CPXmipopt(env, lp) != 0          # no objective of the model is set: refused
+    assert cpx.CPXgetstat(env, lp) == 0
+    x = (C.c_double * n)(*([7.0] * n))
+    assert cpx.CPXgetx(env, lp, x, 0, n - 1) != 0 and list(x) == [0.0] * n
+    obj = C.c_double()
+    assert cpx.CPXgetobjval(env, lp, C.byref(obj)) != 0
+    close_problem(cpx, env, lp)
+
+
+def test_shim_without_gpu_fails_loudly(cpx, lib, examples):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from oracle.lpformat import read_model
+    path = examples["3KP10"]["path"]
+    model = read_model(path)
+    env, lp = open_problem(cpx, path)
+    n = model.n
+    assert cpx.CPXchgobj(env, lp, n, (C.c_int * n)(*range(n)), (C.c_double * n)(*[float(v) for v in model.C[0]])) == 0
+    assert cpx.CPXmipopt(env, lp) != 0          # MOIP_ERR_CUDA underneath: there is no CPU solve in the product
+    assert cpx.CPXgetstat(env, lp) == 0
+    close_problem(cpx, env, lp)
+
+
+@needs_aira
+def test_reference_driver_option_parsing(examples, tmp_path):
+    """boost/program_options.hpp stand-in behind the unmodified main() (src/aira.cpp:156-215)."""
+    r = subprocess.run([AIRA, "--help"], capture_output=True, text=True)
+    assert r.returncode == 1 and "--split-normal" in r.stdout and "-t [ --threads ] arg (=1)" in r.stdout
+    r = subprocess.run([AIRA], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "You must pass in a problem file" in r.stderr
+    r = subprocess.run([AIRA, "-p", examples["3KP10"]["path"], "--split-normal", "-t", "13", "-o", str(tmp_path / "o")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "split_normal can only handle at most 12" in r.stderr
+    r = subprocess.run([AIRA, "--no-such-option"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode != 0                    # uncaught boost::program_options::error, as with Boost
+
+
+@needs_aira
+@pytest.mark.parametrize("variant", list(CTEST_OPTS))
+@pytest.mark.parametrize("stem", SMALL)
+def test_reference_ctest_matrix_on_the_test_double(lib, examples, tmp_path, stem, variant):
+    """Host logic only: unmodified reference driver -> seam -> LD_PRELOAD enumeration double (no GPU here)."""
+    if not os.path.exists(FAKE):
+        pytest.skip("oracle/_build/libfake_mip.so not built")
+    out = str(tmp_path / "front.out")
+    r = run_aira(examples[stem]["path"], out, CTEST_OPTS[variant], preload=FAKE, extra_env={"MOIP_B200_SEAM_STATS": "1"})
+    assert r.returncode == 0, r.stderr
+    assert comparable(open(out).read()) == comparable(examples[stem]["out_text"])
+    m = re.search(r"cplex shim: (\d+) CPXmipopt calls", r.stderr)
+    ips = int(re.search(r"(\d+) IPs solved", open(out).read()).group(1))
+    assert m and int(m.group(1)) == ips        # the reference's ipcount (src/aira.cpp:80) counts exactly the seam's calls
+
+
+@needs_aira
+def test_reference_driver_long_option_forms(lib, examples, tmp_path):
+    if not os.path.exists(FAKE):
+        pytest.skip("oracle/_build/libfake_mip.so not built")
+    out = str(tmp_path / "front.out")
+    env = dict(os.environ, LD_PRELOAD=FAKE)
+    r = subprocess.run([AIRA, "--lp=" + examples["4KP10"]["path"], "--output", out, "--thr=3", "--split", "-c2"],
+                       env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert comparable(open(out).read()) == comparable(examples["4KP10"]["out_text"])
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@needs_aira
+@pytest.mark.parametrize("variant", list(CTEST_OPTS))
+@pytest.mark.parametrize("stem", SMALL + ["2KP50"])
+def test_reference_ctest_matrix_on_the_gpu(lib, examples, tmp_path, stem, variant):
+    """The reference's 30 CTest cases with CPLEX replaced at link level by the B200 library: unmodified
+    src/aira.cpp / problem.cpp / cluster.cpp / thread.cpp / solutions.cpp / result.cpp, every CPXmipopt a GPU B&B."""
+    out = str(tmp_path / "front.out")
+    r = run_aira(examples[stem]["path"], out, CTEST_OPTS[variant], extra_env={"MOIP_B200_SEAM_STATS": "1"})
+    assert r.returncode == 0, r.stderr
+    assert comparable(open(out).read()) == comparable(examples[stem]["out_text"]), r.stderr
+    m = re.search(r"(\d+) node LPs, (\d+) LP iterations, (\d+) kernel launches", r.stderr)
+    assert m and int(m.group(3)) > 0, r.stderr  # the GPU did the solving
+
+
+@pytest.mark.gpu
+@needs_aira
+def test_reference_driver_mop_instance_on_the_gpu(lib, examples, tmp_path):
+    """.mop path of the unmodified reference (read_mop_problem + CPXaddrows) with general integer columns."""
+    out = str(tmp_path / "front.out")
+    r = run_aira(examples["moip_2_30_1_knapsack"]["path"], out, [], extra_env={"MOIP_B200_SEAM_STATS": "1"})
+    assert r.returncode == 0, r.stderr
+    assert comparable(open(out).read()) == comparable(examples["moip_2_30_1_knapsack"]["out_text"]), r.stderr
+    ips = int(re.search(r"(\d+) IPs solved", open(out).read()).group(1))
+    golden_ips = int(re.search(r"(\d+) IPs solved", examples["moip_2_30_1_knapsack"]["out_text"]).group(1))
+    assert ips == golden_ips                    # same subproblem sequence as the run that produced the committed .out
