@@ -136,7 +136,11 @@ def main():
     ap.add_argument("--no-fronts", action="store_true")
     ap.add_argument("--front-instance", default="ap3_30_1", help="synthetic instance of tests/golden/synthetic.json whose "
                     "Pareto front is timed with the EPP strips sharded over the ranks (ap3_12_1, ap3_15_1, ap3_20_1, kp4_25_1 ...)")
-    ap.add_argument("--front-strips-per-gpu", type=int, default=12)
+    ap.add_argument("--front-strips-per-gpu", type=int, default=0,
+                    help="EPP strips per GPU for the synthetic front (12 solver contexts per GPU draw them dynamically); "
+                         "0 = 24 on one GPU (two strips per context even out the strips' very different sizes: 3AP n=30 "
+                         "21.6 s at 12 strips, 18.2 s at 24, 17.7 s at 36, profiles/r01_front_strips.md), 12 per GPU on "
+                         "several GPUs (the configuration of profiles/r01_scaling.md)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -296,9 +300,10 @@ def main():
     print_line = rank == 0
     if not args.no_fronts:
         ctx.close()
-        fr = synthetic_front(args.front_instance, args.front_strips_per_gpu * world, local, tmp)   # collective: every rank
+        per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else (24 if world == 1 else 12)
+        fr = synthetic_front(args.front_instance, per_gpu * world, local, tmp)   # collective: every rank
         if print_line:
-            line.setdefault("time_to_front_s", {})[f"{args.front_instance} --split -t {args.front_strips_per_gpu * world}"] = fr
+            line.setdefault("time_to_front_s", {})[f"{args.front_instance} --split -t {per_gpu * world}"] = fr
     if print_line:
         print(json.dumps(line))
     if dist is not None:
