@@ -73,10 +73,17 @@ void finish(Row& R, int n) {
 }
 }  // namespace
 
-extern "C" int moip_device_count(void) { return 1; }
+// FAKE_MIP_DEVICES=G pretends G devices are visible and FAKE_MIP_LOG_DEVICES=1 prints the device of every context, so
+// that the seam's placement of worker contexts over GPUs (MOIP_B200_DEVICE / MOIP_B200_DEVICES) is testable on the CPU.
+extern "C" int moip_device_count(void) {
+  const char* s = std::getenv("FAKE_MIP_DEVICES");
+  return (s && *s) ? std::atoi(s) : 1;
+}
 
-extern "C" int moip_ctx_create_own_stream(moip_model* m, int /*device*/, moip_ctx** out) {
+extern "C" int moip_ctx_create_own_stream(moip_model* m, int device, moip_ctx** out) {
   if (!m || !out) return MOIP_ERR_ARG;
+  if (device < 0 || device >= moip_device_count()) return MOIP_ERR_ARG;
+  if (std::getenv("FAKE_MIP_LOG_DEVICES")) std::fprintf(stderr, "fake_mip_backend: context on device %d\n", device);
   moip_ctx* c = new moip_ctx();
   c->model = m;
   if (moip_model_get_info(m, &c->info)) return MOIP_ERR_ARG;

@@ -40,6 +40,26 @@ def test_no_gpu_means_loud_failure(lib, examples):
         lib.WorkerPool(pr, 0, 2)
 
 
+def test_seam_primitives_validate_arguments_and_need_a_gpu(lib, examples):
+    """moip_mip_solve / moip_ctx_create_own_stream / moip_device_count (the three entry points behind Seam 1's CPXmipopt):
+    argument errors are reported as MOIP_ERR_ARG; without a device the context cannot be created (no CPU solve)."""
+    import ctypes as C
+    import torch
+    L = lib._lib
+    pr = lib.Problem(examples["3KP10"]["path"])
+    rhs = (C.c_double * 3)(1e20, 1e20, 1e20)
+    st = C.c_int(0)
+    assert L.moip_mip_solve(None, 0, rhs, None, None, None, C.byref(st)) == 1          # MOIP_ERR_ARG: no context
+    h = C.c_void_p()
+    assert L.moip_ctx_create_own_stream(None, 0, C.byref(h)) == 1
+    assert L.moip_ctx_create_own_stream(pr._h, 0, None) == 1
+    if torch.cuda.is_available():
+        assert L.moip_device_count() >= 1
+    else:
+        assert L.moip_device_count() == 0
+        assert L.moip_ctx_create_own_stream(pr._h, 0, C.byref(h)) == 3 and not h.value  # MOIP_ERR_CUDA
+
+
 @pytest.mark.parametrize("stem", SMALL + ["2KP50", "moip_2_30_1_knapsack"])
 def test_loader_matches_oracle_reader(lib, examples, stem):
     path = examples[stem]["path"]

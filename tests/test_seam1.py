@@ -261,6 +261,33 @@ def test_reference_driver_long_option_forms(lib, examples, tmp_path):
     assert comparable(open(out).read()) == comparable(examples["4KP10"]["out_text"])
 
 
+@needs_aira
+def test_seam_spreads_worker_contexts_over_devices(lib, examples, tmp_path):
+    """SURVEY 8e process model: one host thread per worker, each bound to its own GPU.  MOIP_B200_DEVICES=G places the
+    problem objects of the process (main's, then one per worker thread) round-robin on G devices starting at
+    MOIP_B200_DEVICE; checked on the test double, which reports the device every context was created on."""
+    if not os.path.exists(FAKE):
+        pytest.skip("oracle/_build/libfake_mip.so not built")
+    out = str(tmp_path / "front.out")
+
+    def devices(extra):
+        env = {"FAKE_MIP_DEVICES": "8", "FAKE_MIP_LOG_DEVICES": "1"}
+        env.update(extra)
+        for attempt in range(THREADED_RETRIES):
+            r = run_aira(examples["4KP10"]["path"], out, ["-t", "4", "--split"], preload=FAKE, extra_env=env)
+            assert r.returncode == 0, r.stderr
+            if comparable(open(out).read()) == comparable(examples["4KP10"]["out_text"]):
+                break
+        assert comparable(open(out).read()) == comparable(examples["4KP10"]["out_text"])
+        return [int(d) for d in re.findall(r"context on device (\d+)", r.stderr)]
+
+    assert set(devices({})) == {0}                                           # default: everything on device 0
+    assert set(devices({"MOIP_B200_DEVICE": "3"})) == {3}
+    spread = devices({"MOIP_B200_DEVICES": "4"})
+    assert set(spread) == {0, 1, 2, 3} and max(spread.count(d) for d in set(spread)) - min(spread.count(d) for d in set(spread)) <= 1
+    assert set(devices({"MOIP_B200_DEVICE": "6", "MOIP_B200_DEVICES": "4"})) == {6, 7}   # clipped to the visible devices
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @needs_aira
