@@ -247,6 +247,30 @@ def test_reference_ctest_matrix_on_the_test_double(lib, examples, tmp_path, stem
 
 
 @needs_aira
+@pytest.mark.parametrize("kind,k,n,seed,opts", [("kp", 3, 11, 21, []), ("kp", 4, 10, 22, ["-t", "2"]), ("ap", 3, 4, 23, []),
+                                                ("ap", 2, 5, 24, ["-t", "2", "--split"])])
+def test_reference_driver_on_random_instances_against_brute_force(lib, tmp_path, kind, k, n, seed, opts):
+    """Fresh synthetic instances: the front written by the reference driver through the seam equals a brute-force
+    Pareto filter over all feasible points (no generator, no solver involved in the expected value)."""
+    if not os.path.exists(FAKE):
+        pytest.skip("oracle/_build/libfake_mip.so not built")
+    from moip_aira_b200 import instances
+    from oracle import aira_oracle as ao
+    from oracle.lpformat import read_model
+    path = str(tmp_path / f"{kind}{k}_{n}_{seed}.lp")
+    (instances.write_ap if kind == "ap" else instances.write_kp)(path, n, k, seed)
+    m = read_model(path)
+    pts = sorted({tuple(int(v) for v in p) for p in ao.FeasibleSet(m).P})
+    sgn = 1 if m.sense == "MIN" else -1
+    want = sorted([p for p in pts if not any(q != p and all(sgn * q[i] <= sgn * p[i] for i in range(k)) for q in pts)],
+                  reverse=True)
+    golden_text = ("\n" + "\n".join("\t".join(str(v) for v in p) + "\t" for p in want) + "\n\n---\n"
+                   + f"{len(want):8d} Solutions found\n")
+    out = str(tmp_path / "front.out")
+    run_case(path, out, opts, golden_text, preload=FAKE)
+
+
+@needs_aira
 def test_reference_driver_long_option_forms(lib, examples, tmp_path):
     if not os.path.exists(FAKE):
         pytest.skip("oracle/_build/libfake_mip.so not built")
