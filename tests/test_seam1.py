@@ -271,6 +271,33 @@ def test_reference_driver_on_random_instances_against_brute_force(lib, tmp_path,
 
 
 @needs_aira
+def test_reference_tolerance_resolve_is_answered_from_the_previous_solve(lib, examples, tmp_path):
+    """Objective values beyond 1/mip_tolerance make the reference tighten CPXPARAM_MIP_Tolerances_MIPGap and call
+    CPXmipopt again on the unchanged problem (src/aira.cpp:497-503).  The solve behind the seam is exact, so the second
+    call is answered from the first; the front of 3KP10 with every objective scaled by 100 is the golden front x 100."""
+    if not os.path.exists(FAKE):
+        pytest.skip("oracle/_build/libfake_mip.so not built")
+    from oracle.lpformat import parse_out
+    lines = open(examples["3KP10"]["path"]).read().splitlines()
+    scaled = []
+    for l in lines:
+        m = re.match(r"^(.*)>\s*([123])\s*$", l)          # the three objective rows end in "> 1", "> 2", "> 3"
+        if m:
+            l = re.sub(r"(\d+)(\s+x\d+)", lambda t: str(int(t.group(1)) * 100) + t.group(2), m.group(1)) + "> " + m.group(2)
+        scaled.append(l)
+    path = str(tmp_path / "3KP10x100.lp")
+    open(path, "w").write("\n".join(scaled) + "\n")
+    out = str(tmp_path / "front.out")
+    r = run_aira(path, out, [], preload=FAKE, extra_env={"MOIP_B200_SEAM_STATS": "1"})
+    assert r.returncode == 0, r.stderr
+    rows, count = parse_out(open(out).read())
+    assert [tuple(v // 100 for v in row) for row in rows] == [tuple(x) for x in examples["3KP10"]["rows"]]
+    assert all(v % 100 == 0 for row in rows for v in row)
+    m = re.search(r"(\d+) CPXmipopt calls \((\d+) answered from the previous identical solve\), (\d+) IPs", r.stderr)
+    assert m and int(m.group(2)) >= 1 and int(m.group(1)) == int(m.group(2)) + int(m.group(3))
+
+
+@needs_aira
 def test_reference_driver_long_option_forms(lib, examples, tmp_path):
     if not os.path.exists(FAKE):
         pytest.skip("oracle/_build/libfake_mip.so not built")
