@@ -293,10 +293,6 @@ def main():
         if not args.no_fronts:
             line["time_to_front_s"] = time_to_front(mb, local, stream.cuda_stream)
             line["cpu_baseline"]["front"] = cpu_front("ap3_10_1", mb, local, stream.cuda_stream, tmp)
-            try:                                   # reported beside the library's own driver; never fatal for the bench line
-                line["time_to_front_s"]["seam1_unmodified_reference_driver"] = seam1_fronts()
-            except Exception as e:                 # noqa: BLE001
-                line["time_to_front_s"]["seam1_unmodified_reference_driver"] = {"error": repr(e)[:200]}
     print_line = rank == 0
     if not args.no_fronts:
         ctx.close()
@@ -379,37 +375,6 @@ def synthetic_front(name, strips, device, tmp):
     return {"seconds": float(dt.item()), "front": len(front),
             "matches_golden": ([list(r) for r in front] == g["rows"]) if g else None,
             "ips": int(ips.item()), "workers_per_gpu": be.workers, "n_gpus": world}
-
-
-def seam1_fronts():
-    """The reference's own driver, unmodified, linked against the CPLEX stand-in of moip_aira_b200/seam1 (every CPXmipopt is a
-    GPU branch and bound): elapsed seconds from its .out footer (includes CUDA start-up of the process), front checked
-    against the committed golden.  Skipped when the binary (built from /root/reference by oracle/Makefile) is absent."""
-    import re
-    import subprocess
-    exe = os.path.join(ROOT, "oracle", "_ref", "aira_seam1")
-    if not os.path.exists(exe):
-        return {"skipped": "oracle/_ref/aira_seam1 not built"}
-    with open(os.path.join(ROOT, "tests", "golden", "examples.json")) as fh:
-        ex = json.load(fh)
-    tmp = tempfile.mkdtemp(prefix="moip_seam1_")
-    out = {}
-    for stem, opts in (("3KP10", []), ("4AP05", ["-t", "2", "--split"]), ("2KP50", ["-t", "2"])):
-        e = ex[stem]
-        p = os.path.join(tmp, e["file"])
-        with open(p, "w") as fh:
-            fh.write(e["input"])
-        o = os.path.join(tmp, stem + ".out")
-        r = subprocess.run([exe, "-p", p, "-o", o] + opts, capture_output=True, text=True, timeout=120,
-                           env=dict(os.environ, MOIP_B200_SEAM_STATS="1"))
-        text = open(o).read() if os.path.exists(o) else ""
-        keep = lambda t: [" ".join(l.split()) for l in t.splitlines() if not re.search(r"seconds|solved|Using", l)]
-        el = re.search(r"([\d.]+) elapsed seconds", text)
-        kl = re.search(r"(\d+) kernel launches", r.stderr)
-        out[(stem + " " + " ".join(opts)).strip()] = {
-            "seconds": float(el.group(1)) if el else None, "rc": r.returncode, "matches_golden": keep(text) == keep(e["out"]),
-            "kernel_launches": int(kl.group(1)) if kl else None}
-    return out
 
 
 def time_to_front(mb, device, stream):

@@ -1,6 +1,7 @@
-"""Time-to-front of the UNMODIFIED reference driver (oracle/_ref/aira_seam1) on the GPU library, synthetic instances of
+"""TEST UTILITY (not collected by pytest, not part of the product or of bench.py).
+Time-to-front of the UNMODIFIED reference driver (oracle/_ref/aira_seam1) on the GPU library, synthetic instances of
 SURVEY 8d-4/5, every front compared with its committed golden.  Writes one JSON object per run to stdout.
-Usage: python tools/seam1_front_times.py [--big]   (--big adds 3AP n=30 and 4KP n=40 with --split -t 12)"""
+Usage: python tests/seam1_front_times.py [--big]   (--big adds 3AP n=30 and 4KP n=40 with --split -t 12)"""
 import json
 import os
 import re
