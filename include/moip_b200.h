@@ -8,6 +8,10 @@
  * no exceptions across the boundary, one context per worker thread (a context is used by its
  * owner only; several contexts may share one GPU).
  *
+ * The link-level boundary ("Seam 1": the 23 CPX* functions the unmodified reference objects import, src/env.h:4-10)
+ * is declared in moip_aira_b200/seam1/include/ilcplex/cplex.h and implemented on top of this header by
+ * moip_aira_b200/seam1/cpx_shim.cpp (libcplex_moip_b200.so); see INTEGRATION.md.
+ *
  * There is no CPU fallback behind any compute entry point: they return MOIP_ERR_CUDA when no
  * sm_100 device / kernel image is usable.
  */
