@@ -216,6 +216,23 @@ int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, const doubl
  * concurrently on the pool; rows_out = sorted, de-duplicated front */
 int moip_pool_pareto_front(moip_pool* p, int num_threads, int split_normal, int* rows_out, int cap, int* n_rows);
 
+/* ---- cooperative ("synergistic") workers: main() with -t W and no --split (src/aira.cpp:277-308), with a defined,
+ * race-free replacement for the bound-sharing cells of src/aira.cpp:923-1086 / :1111-1552.  Worker i runs
+ * the sequential generator with a permutation whose last objective it OWNS; when the top-level bound of its last
+ * stage moves, it publishes that bound as a monotone limit (one 64-bit atomic per objective) and every other worker
+ * intersects its subproblems with it.  No waiting, no locks; a stale limit only costs redundant work (csrc/generator.cpp). */
+/* W <= k workers, worker i = i-th rotation of the identity permutation (owns objective (k-1-i) mod k) */
+int moip_coop_workers(int k, int n_workers, moip_worker* out);
+/* host-logic hook like moip_optimise_with: the W workers run on W host threads and call solve/find/insert with
+ * users[i] (the callbacks must be thread-safe); n_solves[i] / n_skipped[i] = subproblems worker i handed to solve /
+ * answered as infeasible because a partner had finished */
+int moip_coop_optimise_with(int k, int sense, int n_workers, const moip_worker* workers, moip_solve_fn solve,
+                            moip_find_cb find, moip_insert_cb insert, void* const* users, int64_t* n_solves,
+                            int64_t* n_skipped);
+/* the product path: worker i on solver context i of the pool (one GPU), shared infeasible records, per-worker solution
+ * records; rows_out = sorted, de-duplicated front.  n_workers is clipped to min(k, pool workers). */
+int moip_pool_synergistic_front(moip_pool* p, int n_workers, int* rows_out, int cap, int* n_rows);
+
 const char* moip_version(void);
 
 #ifdef __cplusplus

@@ -107,6 +107,10 @@ _SIGS = {
     "moip_pool_run_strips": (_i, [_vp, _i, _i, _pd, _pi, _i, _pi]),
     "moip_pool_run_strips_claim": (_i, [_vp, _i, _i, _pd, CLAIM_FN, _vp, _pi, _i, _pi]),
     "moip_pool_pareto_front": (_i, [_vp, _i, _i, _pi, _i, _pi]),
+    "moip_coop_workers": (_i, [_i, _i, C.POINTER(Worker)]),
+    "moip_coop_optimise_with": (_i, [_i, _i, _i, C.POINTER(Worker), SOLVE_FN, FIND_CB, INSERT_CB, C.POINTER(_vp),
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "moip_pool_synergistic_front": (_i, [_vp, _i, _pi, _i, _pi]),
     "moip_version": (C.c_char_p, []),
 }
 EXPORTED = sorted(_SIGS)
@@ -330,6 +334,19 @@ class WorkerPool:
     def workers(self):
         return _lib.moip_pool_workers(self._h)
 
+    def synergistic_front(self, n_workers=None, cap=1 << 16):
+        """-t W without --split on the cooperative workers (moip_pool_synergistic_front): W <= k workers, one solver
+        context each, exchanging monotone limits on the objective each of them owns."""
+        k = self.problem.objcnt
+        w = int(n_workers or k)
+        while True:
+            rows = np.zeros((cap, k), dtype=np.int32)
+            n = C.c_int(0)
+            _check(_lib.moip_pool_synergistic_front(self._h, w, _ip(rows), cap, C.byref(n)), "pool_synergistic_front")
+            if n.value <= cap:
+                return [tuple(int(v) for v in r) for r in rows[:n.value]]
+            cap = n.value
+
     def get_limit(self, obj, rhs, sense=None):
         k = self.problem.objcnt
         r = np.ascontiguousarray(rhs, dtype=np.float64)
@@ -487,6 +504,50 @@ def optimise_with(k, sense, worker, solve, find, insert):
     _check(_lib.moip_optimise_with(k, int(sense), C.byref(worker), SOLVE_FN(_solve), FIND_CB(_find),
                                    INSERT_CB(_insert), None, C.byref(it), C.byref(hits)), "optimise_with")
     return it.value, hits.value
+
+
+def coop_workers(k, n_workers):
+    """The W <= k cooperative workers' permutations (worker i owns the last objective of its permutation)."""
+    ws = (Worker * n_workers)()
+    _check(_lib.moip_coop_workers(int(k), int(n_workers), ws), "coop_workers")
+    return [[ws[i].perm[j] for j in range(k)] for i in range(n_workers)]
+
+
+def coop_optimise_with(k, sense, n_workers, solve, find, insert):
+    """Cooperative workers on host threads with caller-supplied solve/find/insert(worker, ...) (host-logic tests).
+    Returns (solves per worker, subproblems skipped per worker)."""
+    ws = (Worker * n_workers)()
+    _check(_lib.moip_coop_workers(int(k), int(n_workers), ws), "coop_workers")
+
+    def _solve(user, perm, n_obj, rhs, result, status):
+        st, res = solve(int(user or 0), [perm[i] for i in range(k)], n_obj, [rhs[i] for i in range(k)])
+        status[0] = st
+        if res is not None:
+            for i in range(k):
+                result[i] = res[i]
+        return 0
+
+    def _find(user, ip, infeasible, result):
+        r = find(int(user or 0), [ip[i] for i in range(k)])
+        if r is None:
+            return 0
+        inf, res = r
+        infeasible[0] = int(inf)
+        if not inf:
+            for i in range(k):
+                result[i] = res[i]
+        return 1
+
+    def _insert(user, ip, result, infeasible):
+        insert(int(user or 0), [ip[i] for i in range(k)], None if infeasible else [result[i] for i in range(k)],
+               bool(infeasible))
+        return 0
+
+    users = (_vp * n_workers)(*[_vp(i) for i in range(n_workers)])
+    solves, skipped = (C.c_int64 * n_workers)(), (C.c_int64 * n_workers)()
+    _check(_lib.moip_coop_optimise_with(int(k), int(sense), int(n_workers), ws, SOLVE_FN(_solve), FIND_CB(_find),
+                                        INSERT_CB(_insert), users, solves, skipped), "coop_optimise_with")
+    return list(solves), list(skipped)
 
 
 def version():

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <climits>
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <cstdint>
 #include <thread>
@@ -26,6 +27,9 @@ struct GenBackend {
   virtual int solve(const int* perm, int n_obj, const double* rhs, int* result, int* status) = 0;
   virtual int find(const double* rhs, int* hit, int* infeasible, int* result) = 0;
   virtual int insert(const double* rhs, const int* result, int infeasible) = 0;
+  // The top-level bound of the LAST stage (objective perm[n_obj-1]) has moved to new_rhs: every non-dominated point
+  // beyond it has been recorded.  Only the cooperative workers (CoopBackend below) listen.
+  virtual void outer_bound_moved(int /*objective*/, double /*new_rhs*/) {}
 };
 
 namespace {
@@ -75,6 +79,7 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
     rhs[objective] = is_min ? (double)wrap32((int64_t)hi_seen[objective] - 1)
                             : (double)wrap32((int64_t)lo_seen[objective] + 1);   // :761-777
     if (split && crossed_stop()) break;                                     // :778-801
+    if (!split && active == n_obj - 1) be.outer_bound_moved(objective, rhs[objective]);
     hi_seen[objective] = INT_MIN;                                           // :802-803
     lo_seen[objective] = INT_MAX;
     while (misses < active) {                                               // :804
@@ -101,6 +106,7 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
         for (int j = 0; j < k; ++j) rhs[j] = free_rhs;                      // :1586-1599
         if (split) rhs[n_obj - 1] = split_start;                            // :1649-1651
         tighten(objective);                                                 // :1655-1673
+        if (!split && active == n_obj - 1) be.outer_bound_moved(objective, rhs[objective]);
         level = 1; depth = perm[level]; walking = false;
       } else if (last_missed && misses != active) {
         rhs[depth] = free_rhs;                                              // :1722-1728
@@ -194,6 +200,155 @@ extern "C" int moip_optimise_with(int k, int sense, const moip_worker* w, moip_s
   if (n_iterations) *n_iterations = 0;
   if (n_hits) *n_hits = 0;
   return run_worker(be, k, sense, *w, n_iterations, n_hits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative ("synergistic") workers: a race-free re-hosting of the idea behind the reference's bound-sharing
+// threads (src/aira.cpp:923-1086, :1111-1552).  Worker w runs the sequential generator above with a
+// permutation whose LAST objective o_w is its own; the W workers own W different objectives.  Whenever the top-level
+// bound of w's last stage moves to b, every non-dominated point with f_{o_w} beyond b is on record (the inner
+// (k-1)-objective front under the previous bound is complete and b = (extreme f_{o_w} over it) -+ 1), so w
+// publishes b as its LIMIT -- one monotone 64-bit atomic per objective.  Every other worker intersects each of its
+// subproblems with f_{o_w} <= b (MIN; >= for MAX) before the cache scan / solve / insert: it stops looking where w
+// has already looked.  Why this is sound without any waiting or locking:
+//   * a limit only ever cuts off a region whose non-dominated points are recorded, and the limits are bounds on
+//     objective VALUES, so the non-dominated points of a restricted set are exactly the non-dominated points of the
+//     full set that lie in it; a worker run against shrinking limits enumerates a superset of what the final
+//     limits require;
+//   * reading a stale (looser) limit only means redundant work, never a lost point; limits are written with
+//     fetch-min / fetch-max, so they are monotone whatever the interleaving;
+//   * cache records are stored under the restricted bound vector actually solved, so Solutions::find's relaxation
+//     test stays exact; infeasible records are valid for every permutation and may be shared;
+//   * a worker that runs to completion has, together with the limits it honoured, covered everything: it publishes
+//     "done" and the others answer their remaining subproblems as infeasible without solving them.
+// The result is the union of the workers' points (all of them lexicographic optima, hence non-dominated).
+namespace moip {
+namespace {
+
+struct CoopShared {
+  int k = 0;
+  bool is_min = true;
+  bool owned[MOIP_MAX_OBJ] = {false, false, false, false};
+  std::atomic<long long> limit[MOIP_MAX_OBJ];
+  static constexpr long long kFree = LLONG_MAX, kDone = LLONG_MIN;   // MIN form; MAX workers publish negated values
+  void init(int k_, bool is_min_) {
+    k = k_; is_min = is_min_;
+    for (int j = 0; j < MOIP_MAX_OBJ; ++j) { limit[j].store(kFree); owned[j] = false; }
+  }
+  // limits are kept in "min form" (value for MIN models, -value for MAX models) so that tighter = smaller
+  void publish(int obj, long long v_minform) {
+    long long cur = limit[obj].load(std::memory_order_relaxed);
+    while (v_minform < cur && !limit[obj].compare_exchange_weak(cur, v_minform, std::memory_order_release,
+                                                               std::memory_order_relaxed)) {}
+  }
+};
+
+struct CoopBackend : GenBackend {
+  GenBackend* inner = nullptr;
+  CoopShared* sh = nullptr;
+  int own = -1;
+  int64_t solves = 0, skipped = 0;
+  double raw[MOIP_MAX_OBJ], clamped[MOIP_MAX_OBJ];
+  bool have = false, dead = false;
+
+  // intersect the generator's bound vector with the partners' published limits
+  void restrict_to_limits(const double* rhs) {
+    const int k = sh->k;
+    if (have && std::memcmp(raw, rhs, sizeof(double) * k) == 0) return;   // find -> solve -> insert of one subproblem
+    dead = false;
+    for (int j = 0; j < k; ++j) {
+      raw[j] = clamped[j] = rhs[j];
+      if (j == own || !sh->owned[j]) continue;
+      const long long L = sh->limit[j].load(std::memory_order_acquire);
+      if (L == CoopShared::kDone) { dead = true; continue; }
+      if (L == CoopShared::kFree) continue;
+      const double lim = sh->is_min ? (double)L : -(double)L;
+      if (sh->is_min ? lim < clamped[j] : lim > clamped[j]) clamped[j] = lim;
+    }
+    have = true;
+  }
+  int solve(const int* perm, int n_obj, const double* rhs, int* result, int* status) override {
+    restrict_to_limits(rhs);
+    if (dead) { ++skipped; *status = MOIP_MIP_INFEASIBLE; return MOIP_OK; }
+    ++solves;
+    return inner->solve(perm, n_obj, clamped, result, status);
+  }
+  int find(const double* rhs, int* hit, int* infeasible, int* result) override {
+    have = false;                                  // a new subproblem: read the limits afresh
+    restrict_to_limits(rhs);
+    if (dead) { *hit = 1; *infeasible = 1; ++skipped; return MOIP_OK; }
+    return inner->find(clamped, hit, infeasible, result);
+  }
+  int insert(const double* rhs, const int* result, int infeasible) override {
+    restrict_to_limits(rhs);
+    if (dead) return MOIP_OK;                      // nothing was solved
+    return inner->insert(clamped, result, infeasible);
+  }
+  void outer_bound_moved(int objective, double new_rhs) override {
+    if (objective != own || std::fabs(new_rhs) >= 2147483647.0) return;   // +-1e20 and the INT_MIN-1 wrap: no claim
+    sh->publish(own, sh->is_min ? (long long)new_rhs : -(long long)new_rhs);
+  }
+  void finished() { sh->limit[own].store(CoopShared::kDone, std::memory_order_release); }
+};
+
+// objective owned by a worker = last entry of its permutation; owners must be distinct
+int coop_check(int k, int n_workers, const moip_worker* ws) {
+  if (n_workers < 1 || n_workers > k) return MOIP_ERR_ARG;
+  bool seen[MOIP_MAX_OBJ] = {false, false, false, false};
+  for (int i = 0; i < n_workers; ++i) {
+    if (ws[i].n_obj != k || ws[i].split) return MOIP_ERR_ARG;
+    bool in_perm[MOIP_MAX_OBJ] = {false, false, false, false};
+    for (int j = 0; j < k; ++j) {
+      if (ws[i].perm[j] < 0 || ws[i].perm[j] >= k || in_perm[ws[i].perm[j]]) return MOIP_ERR_ARG;
+      in_perm[ws[i].perm[j]] = true;
+    }
+    const int o = ws[i].perm[k - 1];
+    if (seen[o]) return MOIP_ERR_ARG;
+    seen[o] = true;
+  }
+  return MOIP_OK;
+}
+
+}  // namespace
+}  // namespace moip
+
+extern "C" int moip_coop_workers(int k, int n_workers, moip_worker* out) {
+  if (!out || k < 1 || k > MOIP_MAX_OBJ || n_workers < 1 || n_workers > k) return MOIP_ERR_ARG;
+  for (int i = 0; i < n_workers; ++i) {            // rotations of the identity: worker i owns objective (k-1-i) mod k
+    out[i] = moip_worker{};
+    out[i].id = i; out[i].n_obj = k; out[i].split = 0;
+    for (int j = 0; j < k; ++j) out[i].perm[j] = ((j - i) % k + k) % k;
+  }
+  return MOIP_OK;
+}
+
+extern "C" int moip_coop_optimise_with(int k, int sense, int n_workers, const moip_worker* workers, moip_solve_fn solve,
+                                       moip_find_cb find, moip_insert_cb insert, void* const* users, int64_t* n_solves,
+                                       int64_t* n_skipped) {
+  if (!workers || !solve || !find || !insert || k < 1 || k > MOIP_MAX_OBJ) return MOIP_ERR_ARG;
+  if (int rc = coop_check(k, n_workers, workers)) return rc;
+  CoopShared sh;
+  sh.init(k, sense == MOIP_SENSE_MIN);
+  for (int i = 0; i < n_workers; ++i) sh.owned[workers[i].perm[k - 1]] = n_workers > 1;
+  std::vector<CallbackBackend> cb(n_workers);
+  std::vector<CoopBackend> co(n_workers);
+  std::vector<int> rcs(n_workers, MOIP_OK);
+  auto work = [&](int i) {
+    cb[i].solve_fn = solve; cb[i].find_fn = find; cb[i].insert_fn = insert; cb[i].user = users ? users[i] : nullptr;
+    co[i].inner = &cb[i]; co[i].sh = &sh; co[i].own = workers[i].perm[k - 1];
+    rcs[i] = run_worker(co[i], k, sense, workers[i], nullptr, nullptr);
+    if (!rcs[i]) co[i].finished();
+  };
+  std::vector<std::thread> th;
+  for (int i = 1; i < n_workers; ++i) th.emplace_back(work, i);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n_workers; ++i) {
+    if (n_solves) n_solves[i] = co[i].solves;
+    if (n_skipped) n_skipped[i] = co[i].skipped;
+    if (rcs[i]) return rcs[i];
+  }
+  return MOIP_OK;
 }
 
 extern "C" int moip_split_strips(int sense, int biggest, int smallest, int num_threads, int split_normal,
@@ -466,6 +621,56 @@ extern "C" int moip_pool_pareto_front(moip_pool* p, int num_threads, int split_n
   *n_rows = moip_cache_sort_unique(all, rows_out, cap);
   moip_cache_destroy(all);
   return MOIP_OK;
+}
+
+// main() with -t W and no --split (src/aira.cpp:277-308), on the cooperative workers above: worker i runs on solver
+// context i of the pool (own stream, same GPU) with the i-th rotation of the objective order; infeasible records are
+// shared (valid for every permutation, like the reference's shared `infeasibles`, src/aira.cpp:539), solution records
+// are per worker (a lexicographic optimum depends on the permutation).  rows_out = sorted, de-duplicated front.
+extern "C" int moip_pool_synergistic_front(moip_pool* p, int n_workers, int* rows_out, int cap, int* n_rows) {
+  if (!p || p->ctx.empty() || !n_rows) return MOIP_ERR_ARG;
+  const int k = p->ctx[0]->dm.k, sense = p->ctx[0]->model->M.sense;
+  n_workers = std::max(1, std::min(n_workers, std::min(k, (int)p->ctx.size())));
+  std::vector<moip_worker> ws(n_workers);
+  int rc = moip_coop_workers(k, n_workers, ws.data());
+  if (rc) return rc;
+  CoopShared sh;
+  sh.init(k, sense == MOIP_SENSE_MIN);
+  for (int i = 0; i < n_workers; ++i) sh.owned[ws[i].perm[k - 1]] = n_workers > 1;
+  moip_cache* infeasibles = nullptr;
+  std::vector<moip_cache*> sols(n_workers, nullptr);
+  rc = moip_cache_create(p->ctx[0], &infeasibles);
+  for (int i = 0; i < n_workers && !rc; ++i) rc = moip_cache_create(p->ctx[i], &sols[i]);
+  std::vector<int> rcs(n_workers, MOIP_OK);
+  if (!rc) {
+    auto work = [&](int i) {
+      GpuBackend be;
+      be.c = p->ctx[i]; be.infeasibles = infeasibles; be.sols = sols[i]; be.sense = sense;
+      CoopBackend co;
+      co.inner = &be; co.sh = &sh; co.own = ws[i].perm[k - 1];
+      rcs[i] = run_worker(co, k, sense, ws[i], nullptr, nullptr);
+      if (!rcs[i]) co.finished();
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_workers; ++i) th.emplace_back(work, i);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n_workers && !rc; ++i) rc = rcs[i];
+  }
+  if (!rc) {
+    moip_cache* all = nullptr;
+    rc = moip_cache_create(p->ctx[0], &all);
+    if (!rc) {
+      std::vector<double> zero(k, 0.0);
+      for (int i = 0; i < n_workers; ++i)
+        for (auto& r : sols[i]->host) if (!r.infeasible) moip_cache_insert(all, zero.data(), r.result, 0);
+      *n_rows = moip_cache_sort_unique(all, rows_out, cap);
+      moip_cache_destroy(all);
+    }
+  }
+  for (auto* sc : sols) moip_cache_destroy(sc);
+  moip_cache_destroy(infeasibles);
+  return rc;
 }
 
 extern "C" int moip_pareto_front(moip_ctx* c, int split, int num_threads, int split_normal, int* rows_out, int cap,
