@@ -190,7 +190,7 @@ def test_synergistic_front_examples_gpu(lib, examples, stem):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ap3_12_1", "kp4_25_1"])
+@pytest.mark.parametrize("name", ["ap3_12_1", "kp4_20_1"])
 def test_synergistic_front_synthetic_gpu(lib, tmp_path, name):
     from moip_aira_b200 import instances
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "synthetic.json")))[name]
