@@ -176,6 +176,7 @@ def test_coop_finished_partner_stops_the_others(lib, examples):
 
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
+@pytest.mark.timeout(180)
 @pytest.mark.parametrize("stem", ["2AP05", "3KP10", "3AP05", "4KP10", "4AP05"])
 def test_synergistic_front_examples_gpu(lib, examples, stem):
     pr = lib.Problem(examples[stem]["path"])
@@ -190,6 +191,7 @@ def test_synergistic_front_examples_gpu(lib, examples, stem):
 
 
 @pytest.mark.gpu
+@pytest.mark.timeout(300)
 @pytest.mark.parametrize("name", ["ap3_12_1", "kp4_20_1"])
 def test_synergistic_front_synthetic_gpu(lib, tmp_path, name):
     from moip_aira_b200 import instances
