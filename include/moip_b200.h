@@ -229,6 +229,18 @@ int moip_coop_workers(int k, int n_workers, moip_worker* out);
 int moip_coop_optimise_with(int k, int sense, int n_workers, const moip_worker* workers, moip_solve_fn solve,
                             moip_find_cb find, moip_insert_cb insert, void* const* users, int64_t* n_solves,
                             int64_t* n_skipped);
+/* the limits as a handle, for one worker per process (one rank per GPU): a host thread keeps the local handle in step with
+ * the other ranks; publishing is fetch-min / fetch-max, so remote values may be merged in any order, any number of times.
+ * owned_mask bit j: some worker of the job owns objective j.  value: right-hand side of f_obj <= value (MIN) / >= (MAX). */
+typedef struct moip_coop moip_coop;
+int moip_coop_create(int k, int sense, int owned_mask, moip_coop** out);
+void moip_coop_destroy(moip_coop* h);
+int moip_coop_publish(moip_coop* h, int obj, long long value, int done);
+int moip_coop_read(const moip_coop* h, int obj, long long* value, int* state /* 0 none, 1 value, 2 owner done */);
+/* one cooperative worker (w->perm's last objective is the one it owns) on a solver context / on callbacks */
+int moip_coop_optimise(moip_ctx* c, const moip_worker* w, moip_coop* shared, moip_cache* all, moip_cache* infeasibles);
+int moip_coop_optimise_one_with(int k, int sense, const moip_worker* w, moip_coop* shared, moip_solve_fn solve,
+                                moip_find_cb find, moip_insert_cb insert, void* user, int64_t* n_solves, int64_t* n_skipped);
 /* the product path: worker i on solver context i of the pool (one GPU), shared infeasible records, per-worker solution
  * records; rows_out = sorted, de-duplicated front.  n_workers is clipped to min(k, pool workers). */
 int moip_pool_synergistic_front(moip_pool* p, int n_workers, int* rows_out, int cap, int* n_rows);

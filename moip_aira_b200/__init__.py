@@ -111,6 +111,13 @@ _SIGS = {
     "moip_coop_optimise_with": (_i, [_i, _i, _i, C.POINTER(Worker), SOLVE_FN, FIND_CB, INSERT_CB, C.POINTER(_vp),
                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "moip_pool_synergistic_front": (_i, [_vp, _i, _pi, _i, _pi]),
+    "moip_coop_create": (_i, [_i, _i, _i, C.POINTER(_vp)]),
+    "moip_coop_destroy": (None, [_vp]),
+    "moip_coop_publish": (_i, [_vp, _i, C.c_longlong, _i]),
+    "moip_coop_read": (_i, [_vp, _i, C.POINTER(C.c_longlong), _pi]),
+    "moip_coop_optimise": (_i, [_vp, C.POINTER(Worker), _vp, _vp, _vp]),
+    "moip_coop_optimise_one_with": (_i, [_i, _i, C.POINTER(Worker), _vp, SOLVE_FN, FIND_CB, INSERT_CB, _vp,
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "moip_version": (C.c_char_p, []),
 }
 EXPORTED = sorted(_SIGS)
@@ -289,6 +296,10 @@ class Context:
     # ---- generator
     def optimise(self, worker: Worker, all_sols: "Solutions", infeasibles: "Solutions"):
         _check(_lib.moip_optimise(self._h, C.byref(worker), all_sols._h, infeasibles._h), "optimise")
+
+    def coop_optimise(self, worker: Worker, limits: "CoopLimits", all_sols: "Solutions", infeasibles: "Solutions"):
+        """One cooperative worker (owns worker.perm[k-1]) on this context against a limits handle (moip_coop_optimise)."""
+        _check(_lib.moip_coop_optimise(self._h, C.byref(worker), limits._h, all_sols._h, infeasibles._h), "coop_optimise")
 
     def pareto_front(self, split=False, num_threads=1, split_normal=False, cap=1 << 16):
         k = self.problem.objcnt
@@ -504,6 +515,74 @@ def optimise_with(k, sense, worker, solve, find, insert):
     _check(_lib.moip_optimise_with(k, int(sense), C.byref(worker), SOLVE_FN(_solve), FIND_CB(_find),
                                    INSERT_CB(_insert), None, C.byref(it), C.byref(hits)), "optimise_with")
     return it.value, hits.value
+
+
+class CoopLimits:
+    """moip_coop handle: the published limits of the cooperative workers (one monotone value per owned objective)."""
+
+    def __init__(self, k, sense, owned):
+        self.k = int(k)
+        h = _vp()
+        mask = 0
+        for j in owned:
+            mask |= 1 << int(j)
+        _check(_lib.moip_coop_create(self.k, int(sense), mask, C.byref(h)), "coop_create")
+        self._h = h
+
+    def publish(self, obj, value=0, done=False):
+        _check(_lib.moip_coop_publish(self._h, int(obj), int(value), int(bool(done))), "coop_publish")
+
+    def read(self, obj):
+        """-> (state, value): state 0 = no limit yet, 1 = value is the limit, 2 = the owner is through"""
+        v, st = C.c_longlong(0), C.c_int(0)
+        _check(_lib.moip_coop_read(self._h, int(obj), C.byref(v), C.byref(st)), "coop_read")
+        return st.value, v.value
+
+    def close(self):
+        if self._h:
+            _lib.moip_coop_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def coop_optimise_one_with(k, sense, perm, limits, solve, find, insert):
+    """ONE cooperative worker (owns perm[-1]) against a CoopLimits handle, caller-supplied solve/find/insert
+    (host-logic tests of the multi-process driver).  Returns (solves, skipped)."""
+    w = make_worker(k, perm=perm)
+
+    def _solve(user, pm, n_obj, rhs, result, status):
+        st, res = solve([pm[i] for i in range(k)], n_obj, [rhs[i] for i in range(k)])
+        status[0] = st
+        if res is not None:
+            for i in range(k):
+                result[i] = res[i]
+        return 0
+
+    def _find(user, ip, infeasible, result):
+        r = find([ip[i] for i in range(k)])
+        if r is None:
+            return 0
+        inf, res = r
+        infeasible[0] = int(inf)
+        if not inf:
+            for i in range(k):
+                result[i] = res[i]
+        return 1
+
+    def _insert(user, ip, result, infeasible):
+        insert([ip[i] for i in range(k)], None if infeasible else [result[i] for i in range(k)], bool(infeasible))
+        return 0
+
+    solves, skipped = C.c_int64(0), C.c_int64(0)
+    _check(_lib.moip_coop_optimise_one_with(int(k), int(sense), C.byref(w), limits._h, SOLVE_FN(_solve), FIND_CB(_find),
+                                            INSERT_CB(_insert), None, C.byref(solves), C.byref(skipped)),
+           "coop_optimise_one_with")
+    return solves.value, skipped.value
 
 
 def coop_workers(k, n_workers):

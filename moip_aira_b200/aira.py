@@ -122,6 +122,27 @@ class GpuBackend:
     def sequential_front(self):
         return self.ctx.pareto_front()
 
+    def synergistic_local(self, n_workers):
+        """-t N without --split on this rank's GPU alone: min(N, k) cooperative workers on a pool of their own."""
+        w = max(1, min(int(n_workers), self.k))
+        pool = self.mb.WorkerPool(self.problem, self.device, w)
+        try:
+            return pool.synergistic_front(w)
+        finally:
+            self._coop_ips = pool.stats()["ip_solved"]
+            pool.close()
+
+    def coop_worker(self, perm, limits):
+        """This rank's cooperative worker (owns perm[-1]) on this rank's GPU; returns the points it found."""
+        mb = self.mb
+        all_sols, inf = mb.Solutions(self.ctx), mb.Solutions(self.ctx)
+        try:
+            self.ctx.coop_optimise(mb.make_worker(self.k, perm=perm), limits, all_sols, inf)
+            return [tuple(r) for r in all_sols.sort_unique()]
+        finally:
+            all_sols.close()
+            inf.close()
+
     def split_strips(self, biggest, smallest, num_threads, split_normal):
         return self.mb.split_strips(self.sense, biggest, smallest, num_threads, split_normal)
 
@@ -131,7 +152,7 @@ class GpuBackend:
             n += self._ctx.stats()["ip_solved"]
         if self._pool is not None:
             n += self._pool.stats()["ip_solved"]
-        return n
+        return n + getattr(self, "_coop_ips", 0)
 
 
 def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):
@@ -164,6 +185,67 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):
 
     rows = level(k)
     return sorted(set(rows), key=lambda r: tuple(-v for v in r))     # sort_unique (src/aira.cpp:336)
+
+
+def synergistic_front(be, dist: Dist, poll_s: float = 0.001):
+    """`-t W` without --split across ranks: rank r is cooperative worker r (r-th rotation of the objective order, owns
+    its last objective) on its own GPU.  The only exchange while solving is the W published limits -- one small value
+    per owned objective in the job's c10d store, mirrored into the local limits handle by a host thread (publishing is
+    fetch-min / fetch-max, so repeated or reordered updates are harmless) -- and one all-gather of the points at the end.
+    Ranks beyond k (there is one owner per objective) contribute nothing and only take part in the gather."""
+    import threading
+    import moip_aira_b200 as mb
+    k, world, rank = be.k, dist.world, dist.rank
+    workers = min(world, k)
+    perms = mb.coop_workers(k, workers)
+    owned = [p[-1] for p in perms]
+    limits = mb.CoopLimits(k, be.sense, owned if workers > 1 else [])
+    store = None
+    if world > 1:
+        from torch.distributed import distributed_c10d
+        store = distributed_c10d._get_default_store()
+        dist._coop_seq = getattr(dist, "_coop_seq", 0) + 1
+        key = lambda j: "moip_coop_%d_%d" % (dist._coop_seq, j)      # noqa: E731
+        if rank < workers:
+            store.set(key(owned[rank]), "free")
+        dist.barrier()                                               # every owner's key exists before anybody reads
+    stop = threading.Event()
+
+    def mirror():
+        last = None
+        while True:
+            final = stop.is_set()
+            if rank < workers:                                       # my own limit -> store
+                st, v = limits.read(owned[rank])
+                cur = "done" if st == 2 else ("free" if st == 0 else str(v))
+                if cur != last:
+                    store.set(key(owned[rank]), cur)
+                    last = cur
+            for w in range(workers):                                 # the others' limits -> my handle
+                if w == rank:
+                    continue
+                val = store.get(key(owned[w])).decode()
+                if val == "done":
+                    limits.publish(owned[w], done=True)
+                elif val != "free":
+                    limits.publish(owned[w], int(val))
+            if final:
+                return
+            time.sleep(poll_s)
+
+    th = None
+    if store is not None:
+        th = threading.Thread(target=mirror, daemon=True)
+        th.start()
+    try:
+        rows = be.coop_worker(perms[rank], limits) if rank < workers else []
+    finally:
+        stop.set()
+        if th is not None:
+            th.join()
+    rows = dist.allgather_rows(rows, k)
+    limits.close()
+    return sorted(set(rows), key=lambda r: tuple(-v for v in r))
 
 
 def format_out(front, cpu_s, wall_s, ips, tag):
@@ -208,13 +290,19 @@ def main(argv=None, backend_factory=None):
         print("Error: at most 4 objectives are supported.", file=sys.stderr)
         return 2
     t0, c0 = time.monotonic(), time.process_time()
-    if args.split or args.threads > 1 or dist.world > 1:
+    coop = bool(os.environ.get("MOIP_SYNERGISTIC")) and not args.split and (args.threads > 1 or dist.world > 1)
+    if coop:
+        # -t N without --split, opt-in (MOIP_SYNERGISTIC=1): the cooperative workers of csrc/generator.cpp -- one per rank
+        # (one GPU each) under torchrun, else min(N, k) workers on this GPU's pool
+        front = synergistic_front(be, dist) if dist.world > 1 else be.synergistic_local(args.threads)
+    elif args.split or args.threads > 1 or dist.world > 1:
         # -t N without --split is the reference's synergistic mode (N permutation workers exchanging bounds,
-        # src/aira.cpp:923-1552).  That protocol is not re-hosted; the N workers are run as N EPP strips instead,
-        # which yields the same front (only IP counts and timing differ, as they do between the reference's modes).
+        # src/aira.cpp:923-1552).  Until the cooperative workers (MOIP_SYNERGISTIC=1) have a measured time-to-front on
+        # the GPU, the default runs the N workers as N EPP strips, which yields the same front (only IP counts and
+        # timing differ, as they do between the reference's modes).
         if not args.split and dist.rank == 0:
-            print("note: -t %d without --split: the workers run as EPP strips (same front; the bound-sharing "
-                  "protocol of the synergistic mode is not re-hosted)" % args.threads, file=sys.stderr)
+            print("note: -t %d without --split: the workers run as EPP strips (same front; set MOIP_SYNERGISTIC=1 for "
+                  "the cooperative workers)" % args.threads, file=sys.stderr)
         front = epp_front(be, dist, max(1, args.threads, dist.world), args.split_normal)
     else:
         front = be.sequential_front()

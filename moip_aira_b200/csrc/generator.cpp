@@ -312,6 +312,77 @@ int coop_check(int k, int n_workers, const moip_worker* ws) {
 }  // namespace
 }  // namespace moip
 
+// Limits as a handle of their own: one worker per PROCESS (one rank per GPU) runs against a local handle that a host
+// thread keeps in step with the other ranks (a few int64 values through the job's store / one small collective);
+// publishing is fetch-min, so merging remote values in any order and any number of times is safe.
+struct moip_coop {
+  moip::CoopShared sh;
+};
+
+extern "C" int moip_coop_create(int k, int sense, int owned_mask, moip_coop** out) {
+  if (!out || k < 1 || k > MOIP_MAX_OBJ || (sense != MOIP_SENSE_MIN && sense != MOIP_SENSE_MAX)) return MOIP_ERR_ARG;
+  moip_coop* h = new moip_coop();
+  h->sh.init(k, sense == MOIP_SENSE_MIN);
+  for (int j = 0; j < k; ++j) h->sh.owned[j] = (owned_mask >> j) & 1;
+  *out = h;
+  return MOIP_OK;
+}
+extern "C" void moip_coop_destroy(moip_coop* h) { delete h; }
+
+// value is in the model's own terms (the right-hand side of f_obj <= value for MIN, >= for MAX); done != 0: the owner is through
+extern "C" int moip_coop_publish(moip_coop* h, int obj, long long value, int done) {
+  if (!h || obj < 0 || obj >= h->sh.k) return MOIP_ERR_ARG;
+  if (done) h->sh.limit[obj].store(CoopShared::kDone, std::memory_order_release);
+  else h->sh.publish(obj, h->sh.is_min ? value : -value);
+  return MOIP_OK;
+}
+// state: 0 = no limit yet, 1 = *value holds the limit, 2 = the owner is through
+extern "C" int moip_coop_read(const moip_coop* h, int obj, long long* value, int* state) {
+  if (!h || obj < 0 || obj >= h->sh.k || !state) return MOIP_ERR_ARG;
+  const long long L = h->sh.limit[obj].load(std::memory_order_acquire);
+  *state = L == CoopShared::kDone ? 2 : (L == CoopShared::kFree ? 0 : 1);
+  if (value) *value = *state == 1 ? (h->sh.is_min ? L : -L) : 0;
+  return MOIP_OK;
+}
+
+// one cooperative worker against a limits handle: the product path (solver context) ...
+extern "C" int moip_coop_optimise(moip_ctx* c, const moip_worker* w, moip_coop* shared, moip_cache* all, moip_cache* infeasibles) {
+  if (!c || !w || !shared || !all || !infeasibles || shared->sh.k != c->dm.k) return MOIP_ERR_ARG;
+  if (int rc0 = coop_check(c->dm.k, 1, w)) return rc0;
+  const int sense = c->model->M.sense, k = c->dm.k;
+  moip_cache* local = nullptr;
+  int rc = moip_cache_create(c, &local);
+  if (rc) return rc;
+  GpuBackend be;
+  be.c = c; be.infeasibles = infeasibles; be.sols = local; be.sense = sense;
+  CoopBackend co;
+  co.inner = &be; co.sh = &shared->sh; co.own = w->perm[k - 1];
+  rc = run_worker(co, k, sense, *w, nullptr, nullptr);
+  if (!rc) {
+    co.finished();
+    moip_cache_sort_unique(local, nullptr, 0);
+    rc = moip_cache_merge(all, local);
+  }
+  moip_cache_destroy(local);
+  return rc;
+}
+// ... and the host-logic hook
+extern "C" int moip_coop_optimise_one_with(int k, int sense, const moip_worker* w, moip_coop* shared, moip_solve_fn solve,
+                                           moip_find_cb find, moip_insert_cb insert, void* user, int64_t* n_solves,
+                                           int64_t* n_skipped) {
+  if (!w || !shared || !solve || !find || !insert || k < 1 || k > MOIP_MAX_OBJ || shared->sh.k != k) return MOIP_ERR_ARG;
+  if (int rc0 = coop_check(k, 1, w)) return rc0;
+  CallbackBackend cb;
+  cb.solve_fn = solve; cb.find_fn = find; cb.insert_fn = insert; cb.user = user;
+  CoopBackend co;
+  co.inner = &cb; co.sh = &shared->sh; co.own = w->perm[k - 1];
+  int rc = run_worker(co, k, sense, *w, nullptr, nullptr);
+  if (!rc) co.finished();
+  if (n_solves) *n_solves = co.solves;
+  if (n_skipped) *n_skipped = co.skipped;
+  return rc;
+}
+
 extern "C" int moip_coop_workers(int k, int n_workers, moip_worker* out) {
   if (!out || k < 1 || k > MOIP_MAX_OBJ || n_workers < 1 || n_workers > k) return MOIP_ERR_ARG;
   for (int i = 0; i < n_workers; ++i) {            // rotations of the identity: worker i owns objective (k-1-i) mod k

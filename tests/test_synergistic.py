@@ -174,6 +174,112 @@ def test_coop_finished_partner_stops_the_others(lib, examples):
     assert all(s <= 1 for s in solves[1:]) and all(sk >= 1 for sk in skipped[1:]), (solves, skipped)
 
 
+class _OracleCoopBackend:
+    """aira.synergistic_front backend for host-logic tests: the oracle's exact solver plays the GPU (one cooperative
+    worker per rank through moip_coop_optimise_one_with); every solve sleeps a little so that the ranks interleave."""
+
+    def __init__(self, path, delay=0.002):
+        import moip_aira_b200 as mb
+        self.mb = mb
+        self.model = read_model(path)
+        self.fs = ao.FeasibleSet(self.model)
+        self.k = self.model.k
+        self.sense = 0 if self.model.sense == "MIN" else 1
+        self.delay = delay
+        self.solves = self.skipped = 0
+
+    def coop_worker(self, perm, limits):
+        inf, sols = ao.Solutions(self.k), ao.Solutions(self.k)
+
+        def solve(pm, n_obj, rhs):
+            time.sleep(self.delay)
+            return self.fs.lex_solve(pm, n_obj, rhs)
+
+        def find(ip):
+            _, r = inf.find(ip, self.model.sense)
+            if r is None:
+                _, r = sols.find(ip, self.model.sense)
+            return None if r is None else (r.infeasible, r.result)
+
+        def insert(ip, res, infeasible):
+            (inf if infeasible else sols).insert(ip, res, infeasible)
+
+        self.solves, self.skipped = self.mb.coop_optimise_one_with(self.k, self.sense, perm, limits, solve, find, insert)
+        return sorted({tuple(r.result) for r in sols.store if not r.infeasible}, reverse=True)
+
+
+def test_coop_limits_handle(lib):
+    lim = lib.CoopLimits(3, 0, [2, 0])                   # MIN: tighter = smaller
+    assert lim.read(2) == (0, 0)
+    lim.publish(2, 50)
+    lim.publish(2, 70)                                   # a stale, looser value never loosens the limit
+    assert lim.read(2) == (1, 50)
+    lim.publish(2, 41)
+    assert lim.read(2) == (1, 41)
+    lim.publish(0, done=True)
+    assert lim.read(0)[0] == 2
+    lim.publish(0, 5)                                    # done is final
+    assert lim.read(0)[0] == 2
+    lim.close()
+    lim = lib.CoopLimits(3, 1, [1])                      # MAX: tighter = larger
+    lim.publish(1, 10)
+    lim.publish(1, 7)
+    lim.publish(1, 12)
+    assert lim.read(1) == (1, 12)
+    with pytest.raises(lib.MoipError):
+        lim.publish(3, 1)
+    lim.close()
+
+
+def test_synergistic_front_single_process_host_logic(lib, examples):
+    """world = 1: one worker, no exchange -- the sequential front."""
+    from moip_aira_b200 import aira
+    be = _OracleCoopBackend(examples["3AP05"]["path"], delay=0.0)
+    assert aira.synergistic_front(be, aira.Dist(None)) == examples["3AP05"]["rows"]
+    assert be.skipped == 0
+
+
+_COOP_RANK_SCRIPT = r'''
+import json, os, sys
+sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+from moip_aira_b200 import aira
+from test_synergistic import _OracleCoopBackend
+dist = aira.Dist(None)
+be = _OracleCoopBackend({path!r})
+front = aira.synergistic_front(be, dist)
+json.dump({{"front": front, "solves": be.solves, "skipped": be.skipped}}, open({out!r} + "." + os.environ["RANK"], "w"))
+import torch.distributed as td
+td.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("stem,world", [("3AP05", 2), ("3AP05", 3), ("4KP10", 4), ("2AP05", 2), ("3KP10", 4)])
+def test_synergistic_front_ranks_gloo(lib, examples, stem, world, tmp_path):
+    """One cooperative worker per rank over gloo (the CPU stand-in for one rank per GPU over NCCL): limits travel through
+    the job's c10d store, the points are all-gathered at the end; every rank ends up with the golden front.  A rank
+    beyond k (3KP10 with 4 ranks) owns nothing and only gathers."""
+    import subprocess
+    import sys
+    e = examples[stem]
+    out = str(tmp_path / "front.json")
+    script = tmp_path / "rank.py"
+    script.write_text(_COOP_RANK_SCRIPT.format(root=ROOT, path=e["path"], out=out))
+    port = 31500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    res = [json.load(open(out + "." + str(r))) for r in range(world)]
+    for r in res:
+        assert [tuple(x) for x in r["front"]] == e["rows"]
+    k = len(e["rows"][0])
+    assert all(r["solves"] == 0 for r in res[k:])        # ranks without an objective of their own do not solve
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.timeout(180)
