@@ -310,3 +310,24 @@ def test_synergistic_front_synthetic_gpu(lib, tmp_path, name):
         assert pool.synergistic_front(pr.objcnt) == [tuple(r) for r in g["rows"]]
     finally:
         pool.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(180)
+def test_coop_worker_on_a_limits_handle_gpu(lib, examples):
+    """moip_coop_optimise on the GPU: the per-rank worker of aira.synergistic_front.  (a) world = 1: no partner, the
+    sequential front; (b) a partner that has published limits and then 'done': the worker only looks where the partner
+    has not, and everything it finds is a point of the golden front inside that region."""
+    from moip_aira_b200 import aira
+    e = examples["3AP05"]
+    be = aira.GpuBackend(e["path"], device=0)
+    assert aira.synergistic_front(be, aira.Dist(None)) == e["rows"]
+    rows = e["rows"]
+    cut = sorted(r[0] for r in rows)[len(rows) // 2]           # pretend the owner of objective 0 has covered f0 > cut
+    lim = lib.CoopLimits(3, 0, [2, 0])
+    lim.publish(0, cut)
+    found = be.coop_worker([0, 1, 2], lim)
+    assert set(found) == {r for r in rows if r[0] <= cut}
+    lim.publish(0, done=True)
+    assert be.coop_worker([0, 1, 2], lim) == []
+    lim.close()
