@@ -298,16 +298,35 @@ def test_synergistic_front_examples_gpu(lib, examples, stem):
 
 @pytest.mark.gpu
 @pytest.mark.timeout(300)
-@pytest.mark.parametrize("name", ["ap3_12_1", "kp4_20_1"])
-def test_synergistic_front_synthetic_gpu(lib, tmp_path, name):
+def test_synergistic_front_synthetic_gpu(lib, tmp_path):
+    """3AP n=12 (263 points, committed golden) with 2 and 3 cooperative workers on one GPU."""
     from moip_aira_b200 import instances
-    g = json.load(open(os.path.join(ROOT, "tests", "golden", "synthetic.json")))[name]
-    path = str(tmp_path / (name + ".lp"))
-    (instances.write_ap if g["kind"] == "ap" else instances.write_kp)(path, g["n"], g["k"], g["seed"])
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "synthetic.json")))["ap3_12_1"]
+    path = str(tmp_path / "ap3_12_1.lp")
+    instances.write_ap(path, g["n"], g["k"], g["seed"])
     pr = lib.Problem(path)
     pool = lib.WorkerPool(pr, 0, pr.objcnt)
     try:
-        assert pool.synergistic_front(pr.objcnt) == [tuple(r) for r in g["rows"]]
+        for workers in (2, 3):
+            assert pool.synergistic_front(workers) == [tuple(r) for r in g["rows"]], workers
+    finally:
+        pool.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("kind,k,n,seed", [("kp", 4, 13, 85), ("kp", 4, 14, 83), ("kp", 3, 15, 84), ("ap", 3, 6, 81)])
+def test_synergistic_front_random_instances_gpu(lib, tmp_path, kind, k, n, seed):
+    """Fresh small instances, k workers on one GPU, against the brute-force Pareto filter (the CPU cases above)."""
+    from moip_aira_b200 import instances
+    path = str(tmp_path / f"{kind}{k}_{n}_{seed}.lp")
+    (instances.write_ap if kind == "ap" else instances.write_kp)(path, n, k, seed)
+    m = read_model(path)
+    want = _nondominated(ao.FeasibleSet(m).P, m.sense == "MIN")
+    pr = lib.Problem(path)
+    pool = lib.WorkerPool(pr, 0, k)
+    try:
+        assert pool.synergistic_front(k) == want
     finally:
         pool.close()
 
