@@ -144,6 +144,24 @@ def test_shim_answers_what_read_lp_problem_asks(cpx, lib, examples, stem):
     assert cpx.CPXchgsense(env, lp, k, conind, sense) == 0                                   # :141
     inf = (C.c_double * k)(*([1e20 if model.sense == "MIN" else -1e20] * k))
     assert cpx.CPXchgrhs(env, lp, k, conind, inf) == 0                                       # :148
+    # structural rows come back as the file has them (CPXgetrows / CPXgetrhs on any row range)
+    ms = model.ms
+    if ms:
+        nzs = int((model.A != 0).sum())
+        sbeg, sind, sval = (C.c_int * ms)(), (C.c_int * max(nzs, 1))(), (C.c_double * max(nzs, 1))()
+        assert cpx.CPXgetrows(env, lp, C.byref(nzcnt), sbeg, sind, sval, nzs, C.byref(surplus), 0, ms - 1) == 0
+        assert nzcnt.value == nzs and surplus.value == 0
+        for r in range(ms):
+            lo, hi = sbeg[r], (nzs if r == ms - 1 else sbeg[r + 1])
+            row = [0.0] * n
+            for e in range(lo, hi):
+                row[sind[e]] = sval[e]
+            assert row == [float(v) for v in model.A[r]]
+        srhs = (C.c_double * ms)()
+        assert cpx.CPXgetrhs(env, lp, srhs, 0, ms - 1) == 0 and list(srhs) == [float(v) for v in model.b]
+        # too little space: CPXERR_NEGATIVE_SURPLUS and the shortfall in *surplus_p, like the callable library
+        assert cpx.CPXgetrows(env, lp, C.byref(nzcnt), sbeg, sind, sval, nzs - 1, C.byref(surplus), 0, ms - 1) == 1207
+        assert surplus.value == -1
     # outside the supported family: loud and nonzero, never a silent wrong answer
     assert cpx.CPXchgsense(env, lp, 1, (C.c_int * 1)(0), b"G" if model.sense == "MIN" else b"L") != 0
     assert cpx.CPXchgrhs(env, lp, 1, (C.c_int * 1)(0), (C.c_double * 1)(3.0)) != 0
