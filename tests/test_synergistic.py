@@ -280,6 +280,53 @@ def test_synergistic_front_ranks_gloo(lib, examples, stem, world, tmp_path):
     assert all(r["solves"] == 0 for r in res[k:])        # ranks without an objective of their own do not solve
 
 
+_INFEASIBLE_LP = """\\ no feasible point: x0 + x1 >= 3 with binaries
+minimize 0
+subject to
+ x0 + x1 >= 3
+ 3 x0 + 2 x1 + 4 x2 > 1
+ 1 x0 + 5 x1 + 2 x2 > 2
+binary
+ x0 x1 x2
+end
+"""
+_SINGLE_POINT_LP = """\\ exactly one feasible point (all ones): objectives 9 and 8
+minimize 0
+subject to
+ x0 + x1 + x2 = 3
+ 3 x0 + 2 x1 + 4 x2 > 1
+ 1 x0 + 5 x1 + 2 x2 > 2
+binary
+ x0 x1 x2
+end
+"""
+
+
+@pytest.mark.parametrize("text,want", [(_INFEASIBLE_LP, []), (_SINGLE_POINT_LP, [(9, 8)])])
+def test_edge_models_host_logic(lib, tmp_path, text, want):
+    """Empty front (infeasible model) and a one-point front through the sequential generator, the cooperative workers
+    and the reference driver behind the seam."""
+    import re
+    import subprocess
+    path = str(tmp_path / "edge.lp")
+    open(path, "w").write(text)
+    m = read_model(path)
+    fs = ao.FeasibleSet(m)
+    assert _nondominated(fs.P, True) == want
+    for workers in (1, 2):
+        pts, solves, skipped = _coop(lib, m, fs, workers)
+        assert pts == want
+    aira = os.path.join(ROOT, "oracle", "_ref", "aira_seam1")
+    fake = os.path.join(ROOT, "oracle", "_build", "libfake_mip.so")
+    if os.path.exists(aira) and os.path.exists(fake):
+        out = str(tmp_path / "edge.out")
+        r = subprocess.run([aira, "-p", path, "-o", out], env=dict(os.environ, LD_PRELOAD=fake), capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        text_out = open(out).read()
+        rows = [tuple(int(v) for v in l.split()) for l in text_out.splitlines() if re.fullmatch(r"\s*-?\d+(\s+-?\d+)*\s*", l)]
+        assert rows == want and f"{len(want)} Solutions found" in text_out
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 @pytest.mark.timeout(180)
@@ -350,3 +397,24 @@ def test_coop_worker_on_a_limits_handle_gpu(lib, examples):
     lim.publish(0, done=True)
     assert be.coop_worker([0, 1, 2], lim) == []
     lim.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("text,want", [(_INFEASIBLE_LP, []), (_SINGLE_POINT_LP, [(9, 8)])])
+def test_edge_models_gpu(lib, tmp_path, text, want):
+    """Empty and one-point fronts on the GPU: sequential generator, EPP strips and cooperative workers."""
+    path = str(tmp_path / "edge.lp")
+    open(path, "w").write(text)
+    pr = lib.Problem(path)
+    ctx = lib.Context(pr, device=0)
+    try:
+        assert ctx.pareto_front() == want
+    finally:
+        ctx.close()
+    pool = lib.WorkerPool(pr, 0, 2)
+    try:
+        assert pool.pareto_front(2) == want
+        assert pool.synergistic_front(2) == want
+    finally:
+        pool.close()
