@@ -300,6 +300,11 @@ def main():
         fr = synthetic_front(args.front_instance, per_gpu * world, local, tmp)   # collective: every rank
         if print_line:
             line.setdefault("time_to_front_s", {})[f"{args.front_instance} --split -t {per_gpu * world}"] = fr
+    if print_line and world == 1 and not args.no_fronts:
+        try:                                       # first GPU timings of the cooperative workers; never fatal for the line
+            line["time_to_front_s"]["cooperative_workers"] = coop_fronts(tmp)
+        except Exception as e:                     # noqa: BLE001
+            line["time_to_front_s"]["cooperative_workers"] = {"error": repr(e)[:200]}
     if print_line:
         print(json.dumps(line))
     if dist is not None:
@@ -375,6 +380,54 @@ def synthetic_front(name, strips, device, tmp):
     return {"seconds": float(dt.item()), "front": len(front),
             "matches_golden": ([list(r) for r in front] == g["rows"]) if g else None,
             "ips": int(ips.item()), "workers_per_gpu": be.workers, "n_gpus": world}
+
+
+_COOP_SCRIPT = r"""
+import json, sys, time
+sys.path.insert(0, sys.argv[1])
+import moip_aira_b200 as mb
+from moip_aira_b200 import instances
+kind, k, n, seed, path = sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), sys.argv[6]
+(instances.write_ap if kind == "ap" else instances.write_kp)(path, n, k, seed)
+pr = mb.Problem(path)
+pool = mb.WorkerPool(pr, 0, k)
+pool.synergistic_front(1)                           # warm-up: CUDA start-up, module load, root LPs
+out = {}
+for w in range(1, k + 1):
+    s0 = pool.stats()
+    t = time.perf_counter()
+    front = pool.synergistic_front(w)
+    dt = time.perf_counter() - t
+    s1 = pool.stats()
+    out[str(w)] = {"seconds": dt, "front": [list(r) for r in front], "ips": s1["ip_solved"] - s0["ip_solved"],
+                   "node_lps": s1["node_lps"] - s0["node_lps"]}
+pool.close()
+print("COOP " + json.dumps(out))
+"""
+
+
+def coop_fronts(tmp, name="ap3_15_1", timeout_s=150):
+    """Cooperative ("synergistic") workers, -t W without --split: time-to-front of a synthetic instance
+    with W = 1..k workers on one GPU, each front checked against the committed golden.  Runs in a child process with a
+    time limit (the path is new on the GPU), so that nothing it does can cost the bench line."""
+    import subprocess
+    g = synthetic_goldens()[name]
+    kind, k, n, seed = parse_instance(name)
+    path = os.path.join(tmp, name + "_coop.lp")
+    try:
+        r = subprocess.run([sys.executable, "-c", _COOP_SCRIPT, ROOT, kind, str(k), str(n), str(seed), path],
+                           capture_output=True, text=True, timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        return {"instance": name, "timeout_s": timeout_s}
+    lines = [l for l in r.stdout.splitlines() if l.startswith("COOP ")]
+    if r.returncode != 0 or not lines:
+        return {"instance": name, "rc": r.returncode, "stderr": r.stderr[-300:]}
+    res = json.loads(lines[-1][5:])
+    out = {"instance": name, "golden_points": len(g["rows"])}
+    for w, d in sorted(res.items()):
+        out["-t " + w] = {"seconds": d["seconds"], "matches_golden": d["front"] == [list(x) for x in g["rows"]],
+                          "ips": d["ips"], "node_lps": d["node_lps"]}
+    return out
 
 
 def time_to_front(mb, device, stream):
