@@ -162,6 +162,17 @@ typedef struct {
 } moip_stats;
 int moip_ctx_stats(const moip_ctx* c, moip_stats* out);
 int moip_ctx_reset_stats(moip_ctx* c);
+/* Device-side split of the solver time per kernel class: the counterpart of the reference's -DFINETIMING split
+ * (src/aira.cpp:554-560, :1868-1876), measured with CUDA events on the context's stream around each class of a B&B round
+ * (K2 propagate + branch, K1 node LPs, K4 round/verify, the round's H2D + D2H blocks) and around each K3 scan.  Off by
+ * default (two event records per class and round); MOIP_KERNEL_TIMING=1 switches it on for every new context. */
+typedef struct {
+  double k1_ms, k2_ms, k3_ms, k4_ms, copy_ms;
+  int64_t rounds;          /* B&B rounds timed */
+  int64_t scans;           /* K3 launches timed */
+} moip_kernel_times;
+int moip_ctx_set_kernel_timing(moip_ctx* c, int on);
+int moip_ctx_kernel_times(const moip_ctx* c, moip_kernel_times* out);
 
 /* ---- subproblem generator re-hosted on the boundary above (src/aira.cpp:538-1884 without the
  * inter-thread bound cells, and the EPP driver src/aira.cpp:1886-1990) -------------------------- */
@@ -202,6 +213,19 @@ int moip_pool_create(moip_model* m, int device, int workers, moip_pool** out);
 void moip_pool_destroy(moip_pool* p);
 int moip_pool_workers(const moip_pool* p);
 int moip_pool_stats(const moip_pool* p, moip_stats* out);                   /* summed over the workers */
+int moip_pool_set_kernel_timing(moip_pool* p, int on);
+int moip_pool_kernel_times(const moip_pool* p, moip_kernel_times* out);     /* summed over the workers */
+/* at most max_workers contexts draw strips in moip_pool_run_strips* (0 = all): several ranks that share one strip counter
+ * each take their share instead of the first rank claiming every strip */
+int moip_pool_set_max_workers(moip_pool* p, int max_workers);
+/* Knowledge exchange between the pools of several ranks while a level's strips are being solved: the records of the
+ * shared `here` / `infeasibles` stores (src/aira.cpp:1918-1933) that this pool produced since the last call (export), and
+ * records produced elsewhere (import).  A record is a fact about the model (src/result.h:10-20) whoever solved it, so the
+ * cache scan (src/solutions.cpp:11-81) stays exact.  Callable from any thread during a run; no-ops between runs. */
+int moip_pool_export_records(moip_pool* p, int cap, double* ip /* cap*k */, int* result /* cap*k */,
+                             int* infeasible /* cap */, int* n_out);
+int moip_pool_import_records(moip_pool* p, int n, const double* ip, const int* result, const int* infeasible);
+int moip_pool_exchange_counts(const moip_pool* p, int64_t* exported, int64_t* imported);
 int moip_pool_get_limit(moip_pool* p, int obj, int sense, const double* rhs, int* result, int* mip_status);
 /* split_optimise (src/aira.cpp:1886-1943) for nstrips explicit (start, stop) pairs, dealt dynamically to
  * the workers; rows_out receives the feasible result vectors (k ints per row, unsorted) */

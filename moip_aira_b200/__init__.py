@@ -50,6 +50,11 @@ class Stats(C.Structure):
                 ("solver_seconds", C.c_double)]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [("k1_ms", C.c_double), ("k2_ms", C.c_double), ("k3_ms", C.c_double), ("k4_ms", C.c_double),
+                ("copy_ms", C.c_double), ("rounds", C.c_int64), ("scans", C.c_int64)]
+
+
 class Worker(C.Structure):
     _fields_ = [("id", C.c_int), ("n_obj", C.c_int), ("perm", C.c_int * MAX_OBJ), ("split", C.c_int),
                 ("split_start", C.c_double), ("split_stop", C.c_double)]
@@ -94,6 +99,14 @@ _SIGS = {
     "moip_mip_solve": (_i, [_vp, _i, _pd, _pi, _pi, C.POINTER(C.c_int64), _pi]),
     "moip_ctx_stats": (_i, [_vp, C.POINTER(Stats)]),
     "moip_ctx_reset_stats": (_i, [_vp]),
+    "moip_ctx_set_kernel_timing": (_i, [_vp, _i]),
+    "moip_ctx_kernel_times": (_i, [_vp, C.POINTER(KernelTimes)]),
+    "moip_pool_set_kernel_timing": (_i, [_vp, _i]),
+    "moip_pool_kernel_times": (_i, [_vp, C.POINTER(KernelTimes)]),
+    "moip_pool_set_max_workers": (_i, [_vp, _i]),
+    "moip_pool_export_records": (_i, [_vp, _i, _pd, _pi, _pi, _pi]),
+    "moip_pool_import_records": (_i, [_vp, _i, _pd, _pi, _pi]),
+    "moip_pool_exchange_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "moip_optimise": (_i, [_vp, C.POINTER(Worker), _vp, _vp]),
     "moip_optimise_with": (_i, [_i, _i, C.POINTER(Worker), SOLVE_FN, FIND_CB, INSERT_CB, _vp,
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -319,6 +332,15 @@ class Context:
     def reset_stats(self):
         _check(_lib.moip_ctx_reset_stats(self._h), "reset_stats")
 
+    def set_kernel_timing(self, on=True):
+        _check(_lib.moip_ctx_set_kernel_timing(self._h, int(bool(on))), "set_kernel_timing")
+
+    def kernel_times(self):
+        """CUDA-event milliseconds per kernel class (the FINETIMING counterpart, reference src/aira.cpp:554-560)"""
+        t = KernelTimes()
+        _check(_lib.moip_ctx_kernel_times(self._h, C.byref(t)), "kernel_times")
+        return {f: getattr(t, f) for f, _ in KernelTimes._fields_}
+
     def close(self):
         if self._h:
             _lib.moip_ctx_destroy(self._h)
@@ -399,6 +421,40 @@ class WorkerPool:
         s = Stats()
         _check(_lib.moip_pool_stats(self._h, C.byref(s)), "pool_stats")
         return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+    def set_kernel_timing(self, on=True):
+        _check(_lib.moip_pool_set_kernel_timing(self._h, int(bool(on))), "pool_set_kernel_timing")
+
+    def kernel_times(self):
+        t = KernelTimes()
+        _check(_lib.moip_pool_kernel_times(self._h, C.byref(t)), "pool_kernel_times")
+        return {f: getattr(t, f) for f, _ in KernelTimes._fields_}
+
+    def set_max_workers(self, n):
+        """at most n contexts draw strips (0 = all): the share of one rank when several ranks draw from one counter"""
+        _check(_lib.moip_pool_set_max_workers(self._h, int(n)), "pool_set_max_workers")
+
+    def export_records(self, cap=1024):
+        """cache records this pool produced since the last call while a level's strips are running -> (ip[n][k], result[n][k], infeasible[n])"""
+        k = self.problem.objcnt
+        ip = np.zeros((cap, k))
+        res = np.zeros((cap, k), dtype=np.int32)
+        inf = np.zeros(cap, dtype=np.int32)
+        n = C.c_int(0)
+        _check(_lib.moip_pool_export_records(self._h, int(cap), _dp(ip), _ip(res), _ip(inf), C.byref(n)), "pool_export_records")
+        return ip[:n.value], res[:n.value], inf[:n.value]
+
+    def import_records(self, ip, result, infeasible):
+        ip = np.ascontiguousarray(ip, dtype=np.float64)
+        res = np.ascontiguousarray(result, dtype=np.int32)
+        inf = np.ascontiguousarray(infeasible, dtype=np.int32)
+        if len(inf):
+            _check(_lib.moip_pool_import_records(self._h, len(inf), _dp(ip), _ip(res), _ip(inf)), "pool_import_records")
+
+    def exchange_counts(self):
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(_lib.moip_pool_exchange_counts(self._h, C.byref(a), C.byref(b)), "pool_exchange_counts")
+        return a.value, b.value
 
     def close(self):
         if self._h:

@@ -4,12 +4,16 @@
 
 Options, defaults, output-file naming and the `.out` layout follow the reference (options :159-188,
 naming :213-221, writer :252, :336-358).  `-c` (CPLEX threads) is accepted and ignored: there is no
-CPLEX.  -t 1 runs the sequential generator on this rank's GPU.  -t N > 1 without --split would be the
-reference's synergistic mode; its inter-worker bound protocol is not re-hosted, so the
-N workers run as N EPP strips instead (same front).  With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded over the ranks
-of a torch.distributed job (one rank per GPU, `torchrun --nproc-per-node G`), with an all-gather of
-the points found between levels; inside a rank the strips run concurrently on a pool of solver
-contexts (MOIP_WORKERS host threads, default 12) that share the GPU.
+CPLEX.  -t 1 runs the sequential generator on this rank's GPU.  -t N > 1 without --split is the reference's
+synergistic mode (src/aira.cpp:277-308): it runs the cooperative workers of csrc/generator.cpp -- min(N, k) workers that
+each own one objective and publish a monotone limit on it (the race-free re-hosting of the bound-sharing protocol,
+SURVEY.md section 8f-3) -- one per rank (one GPU each) under torchrun, else on one GPU's pool of solver contexts.
+With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded over the ranks of a torch.distributed
+job (one rank per GPU, `torchrun --nproc-per-node G`): the ranks draw strips from one job-wide counter, all-gather the
+cache records they produce while they solve (every strip of the job can reuse every other strip's relaxations, like
+the reference's threads share `here` / `infeasibles`, src/aira.cpp:1918-1933) and all-gather the points found between
+levels; inside a rank the strips run concurrently on a pool of solver contexts (MOIP_WORKERS host threads, default 12)
+that share the GPU.  On this backend --split is the faster mode for assignment-type models (profiles/r02_fronts.md).
 """
 from __future__ import annotations
 
@@ -82,6 +86,86 @@ class Dist:
         return lambda: store.add(key, 1) - 1
 
 
+class RecordExchange:
+    """All-gather of newly produced cache records between the ranks WHILE a level's strips are being solved (the
+    reference's strip threads share `here` / `infeasibles` in one address space, src/aira.cpp:1918-1933; SURVEY.md 8e:
+    "all-gather of cache records so strips can reuse each other's relaxations").  A background thread per rank runs the
+    same sequence of fixed-size all-gathers (NCCL on device tensors under torchrun on GPUs, gloo in the CPU tests): every
+    `period_s` it exports what this rank's pool has produced since the last round and imports what the others sent.  The
+    loop ends in the same round on every rank: when all ranks have reported "my strips are done and drained".
+
+        with RecordExchange(dist, endpoint, k):
+            rows = backend.run_strips(...)
+
+    `endpoint` offers export_records(cap) -> (ip[n][k], result[n][k], infeasible[n]) and import_records(ip, result,
+    infeasible); None (or one rank) makes this a no-op."""
+
+    def __init__(self, dist: Dist, endpoint, k, period_s=None, cap=1024):
+        self.dist, self.ep, self.k, self.cap = dist, endpoint, int(k), int(cap)
+        self.period_s = float(os.environ.get("MOIP_EXCHANGE_PERIOD_MS", "15")) * 1e-3 if period_s is None else period_s
+        self.active = dist.world > 1 and endpoint is not None and not os.environ.get("MOIP_NO_EXCHANGE")
+        self.rounds = self.sent = self.received = 0
+        self.error = None
+        self._done = None
+        self._th = None
+
+    def __enter__(self):
+        if self.active:
+            import threading
+            self._done = threading.Event()
+            self._th = threading.Thread(target=self._loop, daemon=True)
+            self._th.start()
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self._done.set()
+            self._th.join()
+            if self.error is not None and exc[0] is None:
+                raise self.error
+        return False
+
+    def _loop(self):
+        try:
+            import torch
+            k, cap, world, rank = self.k, self.cap, self.dist.world, self.dist.rank
+            dev = self.dist.device
+            if dev is not None:
+                torch.cuda.set_device(dev)
+            width = 2 * k + 1
+            host = np.zeros(2 + cap * width)
+            out = [torch.zeros(2 + cap * width, dtype=torch.float64, device=dev if dev is not None else "cpu")
+                   for _ in range(world)]
+            while True:
+                fin = self._done.is_set()                  # read BEFORE the export: nothing is produced after it is set
+                ip, res, inf = self.ep.export_records(cap)
+                n = len(inf)
+                host[0], host[1] = n, 1.0 if (fin and n < cap) else 0.0
+                if n:
+                    rec = host[2:2 + n * width].reshape(n, width)
+                    rec[:, :k], rec[:, k:2 * k], rec[:, 2 * k] = ip, res, inf
+                buf = torch.from_numpy(host[:2 + cap * width].copy())
+                if dev is not None:
+                    buf = buf.to(dev)
+                self.dist.pg.all_gather(out, buf)
+                got = torch.stack(out).cpu().numpy()
+                self.rounds += 1
+                self.sent += n
+                for r in range(world):
+                    m = int(got[r, 0])
+                    if r == rank or m == 0:
+                        continue
+                    rec = got[r, 2:2 + m * width].reshape(m, width)
+                    self.ep.import_records(rec[:, :k], rec[:, k:2 * k].astype(np.int32), rec[:, 2 * k].astype(np.int32))
+                    self.received += m
+                if all(got[r, 1] == 1.0 for r in range(world)):
+                    return
+                if not fin:
+                    time.sleep(self.period_s)
+        except Exception as e:                             # noqa: BLE001  (re-raised by __exit__ on the caller's thread)
+            self.error = e
+
+
 # ------------------------------------------------------------------------------------ backends
 class GpuBackend:
     """Product backend on this rank's B200: one solver context for the sequential generator, a pool of
@@ -114,10 +198,16 @@ class GpuBackend:
         st, res = self.pool.get_limit(obj, rhs)
         return res
 
-    def run_strips(self, n_obj, strips, claim):
+    def run_strips(self, n_obj, strips, claim, share=0):
         """The strips of one EPP level: this rank's workers draw strip indices from `claim` (shared by all ranks),
-        solve them concurrently and share `here`/`infeasibles` like the reference's threads."""
+        solve them concurrently and share `here`/`infeasibles` like the reference's threads.  share > 0: at most that
+        many strips in flight on this rank (its part of the level when there are fewer strips than workers in the job)."""
+        self.pool.set_max_workers(share)
         return self.pool.run_strips(n_obj, strips, claim)
+
+    def exchange_endpoint(self):
+        """what RecordExchange talks to: the pool's export_records / import_records"""
+        return self.pool
 
     def sequential_front(self):
         return self.ctx.pareto_front()
@@ -155,8 +245,9 @@ class GpuBackend:
         return n + getattr(self, "_coop_ips", 0)
 
 
-def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):
-    """split_setup (src/aira.cpp:1945-1990) with each level's strips sharded over the ranks."""
+def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list | None = None):
+    """split_setup (src/aira.cpp:1945-1990) with each level's strips sharded over the ranks.  stats (a list) receives one
+    dict per level: strips, exchange rounds, cache records sent / received by this rank."""
     k = be.k
     is_min = be.sense == 0
     free = [1e20 if is_min else -1e20] * k
@@ -180,7 +271,13 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool):
             if biggest == smallest:
                 smallest = INT_MIN
         strips = be.split_strips(biggest, smallest, num_threads, split_normal)
-        rows = be.run_strips(n_obj, strips, dist.counter("level%d" % n_obj))
+        share = -(-len(strips) // dist.world) if dist.world > 1 else 0      # ceil: no rank claims more than its part at once
+        endpoint = be.exchange_endpoint() if hasattr(be, "exchange_endpoint") else None
+        with RecordExchange(dist, endpoint, k) as ex:
+            rows = be.run_strips(n_obj, strips, dist.counter("level%d" % n_obj), share)
+        if stats is not None:
+            stats.append({"n_obj": n_obj, "strips": len(strips), "exchange_rounds": ex.rounds, "records_sent": ex.sent,
+                          "records_received": ex.received, "rows_here": len(rows)})
         return dist.allgather_rows(rows, k)
 
     rows = level(k)
@@ -266,7 +363,7 @@ def main(argv=None, backend_factory=None):
     ap.add_argument("-t", "--threads", type=int, default=1)
     ap.add_argument("-c", "--cplex_threads", type=int, default=1)
     args = ap.parse_args(argv)
-    if args.split_normal and args.threads > 12:
+    if args.split_normal and args.threads > 12:                       # src/aira.cpp:199-203
         print("Error: split_normal can only handle at most 12 threads.", file=sys.stderr)
         return 1
     if not args.lp:
@@ -290,19 +387,20 @@ def main(argv=None, backend_factory=None):
         print("Error: at most 4 objectives are supported.", file=sys.stderr)
         return 2
     t0, c0 = time.monotonic(), time.process_time()
-    coop = bool(os.environ.get("MOIP_SYNERGISTIC")) and not args.split and (args.threads > 1 or dist.world > 1)
+    strips_for_workers = bool(os.environ.get("MOIP_THREADS_AS_STRIPS"))
+    coop = not args.split and (args.threads > 1 or dist.world > 1) and not strips_for_workers
+    if args.split_normal and max(args.threads, dist.world) > 12:
+        print("Error: split_normal can only handle at most 12 threads (strips: max(-t, ranks)).", file=sys.stderr)
+        return 1
     if coop:
-        # -t N without --split, opt-in (MOIP_SYNERGISTIC=1): the cooperative workers of csrc/generator.cpp -- one per rank
-        # (one GPU each) under torchrun, else min(N, k) workers on this GPU's pool
+        # -t N without --split = the reference's synergistic mode (src/aira.cpp:277-308), its default: the cooperative
+        # workers of csrc/generator.cpp -- one per rank (one GPU each) under torchrun, else min(N, k) workers on this
+        # GPU's pool.  There is one owner per objective, so at most k workers are active (the reference caps at k!).
+        if dist.rank == 0 and max(args.threads, dist.world) > be.k:
+            print("note: %d workers asked for, %d objectives: %d cooperative workers run (one owner per objective); "
+                  "--split -t N uses every thread / GPU" % (max(args.threads, dist.world), be.k, be.k), file=sys.stderr)
         front = synergistic_front(be, dist) if dist.world > 1 else be.synergistic_local(args.threads)
     elif args.split or args.threads > 1 or dist.world > 1:
-        # -t N without --split is the reference's synergistic mode (N permutation workers exchanging bounds,
-        # src/aira.cpp:923-1552).  Until the cooperative workers (MOIP_SYNERGISTIC=1) have a measured time-to-front on
-        # the GPU, the default runs the N workers as N EPP strips, which yields the same front (only IP counts and
-        # timing differ, as they do between the reference's modes).
-        if not args.split and dist.rank == 0:
-            print("note: -t %d without --split: the workers run as EPP strips (same front; set MOIP_SYNERGISTIC=1 for "
-                  "the cooperative workers)" % args.threads, file=sys.stderr)
         front = epp_front(be, dist, max(1, args.threads, dist.world), args.split_normal)
     else:
         front = be.sequential_front()

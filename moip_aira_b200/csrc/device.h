@@ -100,6 +100,18 @@ struct LpParams {
 
 // serialises the one-time cudaFuncSetAttribute blocks of the launchers (worker threads share the kernels)
 std::mutex& launch_cfg_mutex();
+// cudaFuncSetAttribute / the shared-memory carve-out apply to the CURRENT device only: one process may hold contexts on
+// several GPUs (Seam 1 MOIP_B200_DEVICES, one worker per GPU), so every launcher keeps its one-time state per device
+constexpr int kMaxDevices = 64;
+struct LaunchCfg {
+  size_t configured[kMaxDevices] = {};
+  int occ[kMaxDevices] = {};
+};
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+  return d;
+}
 
 int launch_k1_any(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);   // best path the model allows
 int launch_k1_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st);
@@ -132,7 +144,26 @@ int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queri
 // K4
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub,
                     int* xr /*[B][3][n]*/, long long* obj_out /*[B][3][k]*/, unsigned char* feasible_out /*[B][3]*/,
-                    int* first_free /*[B][3]: first unfixed column, its lb, ub (or nullptr)*/, cudaStream_t st);
+                    int* first_free /*[B][3]: first unfixed column, its lb, ub (or nullptr)*/,
+                    const int* skip /*[B] nonzero: node decided by K2, not rounded (or nullptr)*/, cudaStream_t st);
+// Largest grid of the short per-round helper kernels (K2 propagate / K4 round).  Their CTAs are latency-bound and each
+// one that lands on an SM holds registers a K1 CTA of another worker could use (K1: 2 CTAs x 32 K registers fill an SM),
+// so they are kept on few SMs and loop over the nodes instead of spreading one CTA per node (MOIP_AUX_GRID overrides).
+int aux_grid_cap();
+// Shared-memory carve-out of the helper kernels (K2 / K3 / K4), percent, or -1 = the driver's default (MOIP_AUX_CARVEOUT).
+// Kernels with different carve-outs cannot share an SM, and switching an SM over needs it drained.
+int aux_carveout_pct();
+template <class K>
+inline int set_aux_carveout(K kern, LaunchCfg& cfg) {
+  const int pct = aux_carveout_pct();
+  if (pct < 0) return MOIP_OK;
+  std::lock_guard<std::mutex> lk(launch_cfg_mutex());
+  const int dev = current_device();
+  if (cfg.occ[dev] == pct + 1) return MOIP_OK;
+  MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+  cfg.occ[dev] = pct + 1;
+  return MOIP_OK;
+}
 int launch_k4(const DevModel& dm, int B, const int* x, const double* rhs, long long* obj_out,
               unsigned char* feasible_out, cudaStream_t st);
 

@@ -184,7 +184,7 @@ extern "C" int moip_optimise(moip_ctx* c, const moip_worker* w, moip_cache* all,
   GpuBackend be;
   be.c = c; be.infeasibles = infeasibles; be.sols = w->split ? all : local; be.sense = sense;
   rc = run_worker(be, c->dm.k, sense, *w, nullptr, nullptr);
-  if (!rc) {
+  if (!rc && moip_cache_size(local) > 0) {           // (EPP strips write straight into `all`: nothing to splice)
     moip_cache_sort_unique(local, nullptr, 0);       // :1877
     rc = moip_cache_merge(all, local);               // :1879
   }
@@ -516,6 +516,14 @@ struct moip_pool {
   int device = 0;
   std::vector<moip_ctx*> ctx;
   std::vector<cudaStream_t> streams;
+  int max_workers = 0;                       // 0 = every context may draw strips (moip_pool_set_max_workers)
+  // the shared stores of the EPP level being solved (nullptr between runs): what the knowledge exchange between the
+  // pools of several ranks reads and feeds (moip_pool_export_records / moip_pool_import_records)
+  std::mutex run_mu;
+  moip_cache* run_here = nullptr;
+  moip_cache* run_inf = nullptr;
+  size_t exp_cursor[2] = {0, 0};
+  int64_t exported = 0, imported = 0;
 };
 
 extern "C" int moip_pool_create(moip_model* m, int device, int workers, moip_pool** out) {
@@ -549,6 +557,68 @@ extern "C" void moip_pool_destroy(moip_pool* p) {
 
 extern "C" int moip_pool_workers(const moip_pool* p) { return p ? (int)p->ctx.size() : -1; }
 
+extern "C" int moip_pool_set_max_workers(moip_pool* p, int max_workers) {
+  if (!p || max_workers < 0) return MOIP_ERR_ARG;
+  p->max_workers = max_workers;
+  return MOIP_OK;
+}
+
+// ---- knowledge exchange between the pools of several ranks (one rank per GPU).  A cache record states a fact about the
+// model -- "the lexicographic optimum under the bounds ip is result" / "nothing lies inside ip" (src/result.h:10-20) -- that
+// holds whoever computed it, as long as permutation and stage count agree (all strips of an EPP level use the identity
+// permutation and the same n_obj, src/thread.cpp:124-133).  The reference's strip threads share `here` / `infeasibles`
+// inside one process (src/aira.cpp:1918-1933); this is the same sharing across processes.  Both calls may come from any
+// thread while moip_pool_run_strips* is running; between runs there is nothing to exchange.
+extern "C" int moip_pool_export_records(moip_pool* p, int cap, double* ip, int* result, int* infeasible, int* n_out) {
+  if (!p || !n_out || cap < 0 || (cap > 0 && (!ip || !result || !infeasible))) return MOIP_ERR_ARG;
+  *n_out = 0;
+  std::lock_guard<std::mutex> rl(p->run_mu);
+  if (!p->run_here || !p->run_inf) return MOIP_OK;
+  const int k = p->run_here->k;
+  int n = 0;
+  moip_cache* stores[2] = {p->run_inf, p->run_here};        // infeasible records first: they prune the most
+  for (int w = 0; w < 2 && n < cap; ++w) {
+    moip_cache* s = stores[w];
+    std::lock_guard<std::mutex> lk(s->mu);
+    size_t& cur = p->exp_cursor[w];
+    for (; cur < s->host.size() && n < cap; ++cur) {
+      const CacheRecord& r = s->host[cur];
+      if (r.pad[0]) continue;                               // came from another rank
+      for (int j = 0; j < k; ++j) { ip[(size_t)n * k + j] = r.ip[j]; result[(size_t)n * k + j] = r.result[j]; }
+      infeasible[n] = r.infeasible;
+      ++n;
+    }
+  }
+  p->exported += n;
+  *n_out = n;
+  return MOIP_OK;
+}
+
+extern "C" int moip_pool_import_records(moip_pool* p, int n, const double* ip, const int* result, const int* infeasible) {
+  if (!p || n < 0 || (n > 0 && (!ip || !result || !infeasible))) return MOIP_ERR_ARG;
+  std::lock_guard<std::mutex> rl(p->run_mu);
+  if (!p->run_here || !p->run_inf) return MOIP_OK;
+  const int k = p->run_here->k;
+  for (int i = 0; i < n; ++i) {
+    CacheRecord r{};
+    for (int j = 0; j < k; ++j) { r.ip[j] = ip[(size_t)i * k + j]; r.result[j] = infeasible[i] ? 0 : result[(size_t)i * k + j]; }
+    r.infeasible = infeasible[i] ? 1 : 0;
+    r.pad[0] = 1;
+    moip_cache* s = r.infeasible ? p->run_inf : p->run_here;
+    std::lock_guard<std::mutex> lk(s->mu);
+    s->host.push_back(r);
+  }
+  p->imported += n;
+  return MOIP_OK;
+}
+
+extern "C" int moip_pool_exchange_counts(const moip_pool* p, int64_t* exported, int64_t* imported) {
+  if (!p) return MOIP_ERR_ARG;
+  if (exported) *exported = p->exported;
+  if (imported) *imported = p->imported;
+  return MOIP_OK;
+}
+
 extern "C" int moip_pool_stats(const moip_pool* p, moip_stats* out) {
   if (!p || !out) return MOIP_ERR_ARG;
   *out = moip_stats{};
@@ -556,6 +626,23 @@ extern "C" int moip_pool_stats(const moip_pool* p, moip_stats* out) {
     out->ip_solved += c->stats.ip_solved; out->bb_nodes += c->stats.bb_nodes; out->node_lps += c->stats.node_lps;
     out->lp_iterations += c->stats.lp_iterations; out->kernel_launches += c->stats.kernel_launches;
     out->cache_queries += c->stats.cache_queries; out->solver_seconds += c->stats.solver_seconds;
+  }
+  return MOIP_OK;
+}
+
+extern "C" int moip_pool_set_kernel_timing(moip_pool* p, int on) {
+  if (!p) return MOIP_ERR_ARG;
+  for (moip_ctx* c : p->ctx)
+    if (int rc = moip_ctx_set_kernel_timing(c, on)) return rc;
+  return MOIP_OK;
+}
+extern "C" int moip_pool_kernel_times(const moip_pool* p, moip_kernel_times* out) {
+  if (!p || !out) return MOIP_ERR_ARG;
+  *out = moip_kernel_times{};
+  for (moip_ctx* c : p->ctx) {
+    out->k1_ms += c->ktimes.k1_ms; out->k2_ms += c->ktimes.k2_ms; out->k3_ms += c->ktimes.k3_ms;
+    out->k4_ms += c->ktimes.k4_ms; out->copy_ms += c->ktimes.copy_ms; out->rounds += c->ktimes.rounds;
+    out->scans += c->ktimes.scans;
   }
   return MOIP_OK;
 }
@@ -580,7 +667,8 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   if (!p || p->ctx.empty() || nstrips < 0 || (nstrips > 0 && !start_stop) || !n_rows) return MOIP_ERR_ARG;
   const int k = p->ctx[0]->dm.k;
   if (n_obj < 1 || n_obj > k) return MOIP_ERR_ARG;
-  const int W = std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
+  int W = std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
+  if (p->max_workers > 0) W = std::min(W, p->max_workers);
   std::atomic<int> next(0), failed(0);
   // `here` and `infeasibles` are shared by the strips of a level, like the reference's threads share them
   // (src/aira.cpp:1918-1933); MOIP_POOL_PRIVATE_CACHES=1 gives every worker its own pair instead
@@ -590,6 +678,8 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
     int rc0 = moip_cache_create(p->ctx[0], &sh_here);
     if (!rc0) rc0 = moip_cache_create(p->ctx[0], &sh_inf);
     if (rc0) { moip_cache_destroy(sh_here); moip_cache_destroy(sh_inf); return rc0; }
+    std::lock_guard<std::mutex> rl(p->run_mu);
+    p->run_here = sh_here; p->run_inf = sh_inf; p->exp_cursor[0] = p->exp_cursor[1] = 0;
   }
   std::vector<std::vector<int>> found(W);
   auto work = [&](int wi) {
@@ -619,8 +709,12 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   work(0);
   for (auto& t : th) t.join();
   if (shared) {
-    if (!failed.load())
-      for (auto& r : sh_here->host) if (!r.infeasible) found[0].insert(found[0].end(), r.result, r.result + k);
+    {
+      std::lock_guard<std::mutex> rl(p->run_mu);
+      p->run_here = nullptr; p->run_inf = nullptr;
+    }
+    if (!failed.load())      // (records imported from other ranks are reported by the rank that found them)
+      for (auto& r : sh_here->host) if (!r.infeasible && !r.pad[0]) found[0].insert(found[0].end(), r.result, r.result + k);
     moip_cache_destroy(sh_here);
     moip_cache_destroy(sh_inf);
   }

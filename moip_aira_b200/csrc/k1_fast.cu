@@ -445,9 +445,11 @@ template <int NT, int KD, int ELLW, int MINB>
 int launch_fast(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
   auto kern = k1_fast_kernel<NT, KD, ELLW, MINB>;
   const size_t smem = sizeof(double) * ((size_t)CS * dm.n + (size_t)2 * dm.m + (size_t)24 * (NT / 32));
-  static size_t configured = 0;
-  static int occ = 1;
+  static LaunchCfg cfg;
   std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
+  const int dev = current_device();
+  size_t& configured = cfg.configured[dev];
+  int& occ = cfg.occ[dev];
   if (smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // leave the rest of the 256 KB array to L1: the packed model image (tens of KB) is re-read by every

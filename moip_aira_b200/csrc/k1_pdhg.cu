@@ -377,8 +377,9 @@ int launch_nt(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_s
     std::fprintf(stderr, "moip_b200: node LP needs the streaming scratch (n=%d) but none was provided\n", dm.n);
     return MOIP_ERR_LIMIT;
   }
-  static size_t configured = 0;
+  static LaunchCfg cfg;
   std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
+  size_t& configured = cfg.configured[current_device()];
   if (smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(k1_pdhg_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;

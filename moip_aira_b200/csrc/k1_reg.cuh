@@ -623,9 +623,11 @@ int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cu
   const size_t prod_len = ((size_t)dm.msS * dm.RWP + 2 + 1) & ~(size_t)1;
   const size_t smem = kYshBytes + sizeof(double) * (prod_len + 256 + 8 + COLD_N + 2 + (size_t)16 * (NT / 32) + 2 +
                                                     (size_t)4 * NT * CPT + (size_t)(KD + 2) * NT);
-  static size_t configured = 0;
-  static int occ = 1;
+  static LaunchCfg cfg;
   std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
+  const int dev = current_device();
+  size_t& configured = cfg.configured[dev];
+  int& occ = cfg.occ[dev];
   if (smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

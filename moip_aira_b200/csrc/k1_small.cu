@@ -434,9 +434,11 @@ template <int KD, int CPT, int MINB>
 int launch_small(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
   auto kern = k1_small_kernel<KD, CPT, MINB>;
   const size_t smem = (size_t)CPT * 128 * (sizeof(double2) + sizeof(double)) + (size_t)(128 / 8) * COLD_N * sizeof(double);
-  static size_t configured = 0;
-  static int occ = 1;
+  static LaunchCfg cfg;
   std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
+  const int dev = current_device();
+  size_t& configured = cfg.configured[dev];
+  int& occ = cfg.occ[dev];
   if (configured == 0) {
     MOIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MOIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));

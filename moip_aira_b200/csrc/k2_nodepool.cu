@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(kPropThreads) k2_propagate_kernel(const DevMod
     int* plb = pool.lb + (size_t)slot * n;
     int* pub = pool.ub + (size_t)slot * n;
     if (tid == 0) s_infeasible = 0;
+    __syncthreads();                         // the reset must not overtake another warp's "crossed bounds" store below
     for (int j = tid; j < n; j += kPropThreads) {
       const int a = plb[j], b2 = pub[j];
       lb[j] = a; ub[j] = b2; nlb[j] = a; nub[j] = b2;
@@ -174,14 +175,18 @@ int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const i
                         const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st) {
   if (B <= 0) return MOIP_OK;
   const size_t smem = sizeof(int) * 4 * (size_t)dm.n;
-  static size_t configured = 0;
+  static LaunchCfg cfg;
   std::unique_lock<std::mutex> cfg_lock(launch_cfg_mutex());
+  size_t& configured = cfg.configured[current_device()];
   if (smem > 48 * 1024 && smem > configured) {
     MOIP_CUDA(cudaFuncSetAttribute(k2_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   cfg_lock.unlock();
-  int grid = B < 148 * 8 ? B : 148 * 8;
+  static LaunchCfg carve;
+  if (set_aux_carveout(k2_propagate_kernel, carve)) return MOIP_ERR_CUDA;
+  const int gcap = aux_grid_cap();
+  int grid = B < gcap ? B : gcap;
   k2_propagate_kernel<<<grid, kPropThreads, smem, st>>>(dm, pool, B, ids, obj_lo, obj_hi, max_rounds, flag, leaf_obj);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
@@ -189,6 +194,8 @@ int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const i
 
 int launch_k2_branch(const DevModel& dm, const PoolView& pool, int C, const BranchOp* ops, cudaStream_t st) {
   if (C <= 0) return MOIP_OK;
+  static LaunchCfg carve;
+  if (set_aux_carveout(k2_branch_kernel, carve)) return MOIP_ERR_CUDA;
   int grid = C < 148 * 8 ? C : 148 * 8;
   k2_branch_kernel<<<grid, 128, 0, st>>>(dm, pool, C, ops);
   MOIP_CUDA(cudaGetLastError());

@@ -115,13 +115,14 @@ __global__ void __launch_bounds__(128) k4_verify_kernel(const DevModel dm, int B
 // each candidate exactly; one warp per (node, candidate).  Feeds the incumbent search of the B&B.
 __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm, int B, const int* slot, const double* wx,
                                                               const int* lb, const int* ub, int* xr, long long* obj_out,
-                                                              unsigned char* feasible_out, int* first_free) {
+                                                              unsigned char* feasible_out, int* first_free, const int* skip) {
   const int lane = threadIdx.x & 31;
   const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int n = dm.n;
   for (int w = wglobal; w < B * 3; w += nwarps) {
     const int node = w / 3, mode = w - node * 3;
+    if (skip && skip[node]) continue;      // decided by K2 (infeasible / leaf): nobody reads its roundings
     const size_t srow = slot ? (size_t)slot[node] : (size_t)node;
     int* xp = xr + (size_t)w * n;
     long long obj[MOIP_MAX_OBJ] = {0, 0, 0, 0};
@@ -166,11 +167,14 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
 }  // namespace
 
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub, int* xr,
-                    long long* obj_out, unsigned char* feasible_out, int* first_free, cudaStream_t st) {
+                    long long* obj_out, unsigned char* feasible_out, int* first_free, const int* skip, cudaStream_t st) {
   if (B <= 0) return MOIP_OK;
   int blocks = (B * 3 + 3) / 4;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out, first_free);
+  static LaunchCfg carve;
+  if (set_aux_carveout(k4_round_verify_kernel, carve)) return MOIP_ERR_CUDA;
+  const int cap = aux_grid_cap();
+  if (blocks > cap) blocks = cap;
+  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out, first_free, skip);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }
@@ -178,6 +182,8 @@ int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx
 int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queries, int sense, int* first_match,
               int* which, cudaStream_t st) {
   if (Q <= 0) return MOIP_OK;
+  static LaunchCfg carve;
+  if (set_aux_carveout(k3_scan_kernel<128>, carve)) return MOIP_ERR_CUDA;
   int grid = Q < 148 * 16 ? Q : 148 * 16;
   k3_scan_kernel<128><<<grid, 128, 0, st>>>(c0, c1, Q, queries, sense, first_match, which);
   MOIP_CUDA(cudaGetLastError());

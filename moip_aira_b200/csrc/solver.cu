@@ -17,6 +17,23 @@ std::mutex& moip::launch_cfg_mutex() {
   return m;
 }
 
+int moip::aux_carveout_pct() {
+  static const int pct = [] {
+    const char* s = std::getenv("MOIP_AUX_CARVEOUT");
+    return s ? std::atoi(s) : -1;
+  }();
+  return pct;
+}
+
+int moip::aux_grid_cap() {
+  static const int cap = [] {
+    const char* s = std::getenv("MOIP_AUX_GRID");
+    const int v = s ? std::atoi(s) : 0;
+    return v > 0 ? v : 148 * 8;
+  }();
+  return cap;
+}
+
 namespace {
 
 template <class T>
@@ -121,7 +138,32 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->bb_check = env_int("MOIP_BB_CHECK", 32);
   c->norm_every = env_int("MOIP_NORM_EVERY", 16);
   c->bb_levels = env_int("MOIP_BB_LEVELS", 3);
+  c->use_points = env_int("MOIP_POINT_STORE", 1) != 0;
+  {
+    std::unique_lock<std::shared_mutex> lk(m->points.mu);
+    if (m->points.n == 0) {
+      bool narrow = true;
+      for (int j = 0; j < M.n; ++j) narrow = narrow && M.lbI[j] >= -127 && M.ubI[j] <= 127;
+      m->points.init(M.n, M.k, narrow);
+    }
+  }
+  if (env_int("MOIP_KERNEL_TIMING", 0) && moip_ctx_set_kernel_timing(c, 1)) { moip_ctx_destroy(c); return MOIP_ERR_CUDA; }
   *out = c;
+  return MOIP_OK;
+}
+
+extern "C" int moip_ctx_set_kernel_timing(moip_ctx* c, int on) {
+  if (!c) return MOIP_ERR_ARG;
+  MOIP_CUDA(cudaSetDevice(c->device));
+  if (on && !c->kev[0])
+    for (auto& e : c->kev) MOIP_CUDA(cudaEventCreate(&e));
+  c->ktiming = on != 0;
+  c->kev_branch_pending = false;
+  return MOIP_OK;
+}
+extern "C" int moip_ctx_kernel_times(const moip_ctx* c, moip_kernel_times* out) {
+  if (!c || !out) return MOIP_ERR_ARG;
+  *out = c->ktimes;
   return MOIP_OK;
 }
 
@@ -133,6 +175,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
                  1e6 * c->prof_t[2] / c->prof_t[3]);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (auto& e : c->kev) if (e) cudaEventDestroy(e);
   for (void* p : c->model_allocs) cudaFree(p);
   c->b_cost.release(); c->b_lb.release(); c->b_ub.release(); c->b_status.release(); c->b_iters.release();
   c->b_branch.release(); c->b_counter.release(); c->b_rhs.release(); c->b_pobj.release(); c->b_dbound.release();
@@ -339,6 +382,7 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
   if (s0 && s0->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
   if (s1 && s1->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
   if (c->q_ip.ensure((size_t)Q * k) || c->q_out.ensure(Q) || c->q_which.ensure(Q) || c->h_q.ensure((size_t)2 * Q)) return MOIP_ERR_CUDA;
+  c->kmark(8);
   MOIP_CUDA(cudaMemcpyAsync(c->q_ip.p, ip, sizeof(double) * Q * k, cudaMemcpyHostToDevice, c->stream));
   DevCache e{}; e.k = k; e.size = 0; e.rec = nullptr;
   int rc = launch_k3(s0 ? s0->view() : e, s1 ? s1->view() : e, Q, c->q_ip.p, sense, c->q_out.p, c->q_which.p, c->stream);
@@ -347,7 +391,9 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
   c->stats.cache_queries += Q;
   MOIP_CUDA(cudaMemcpyAsync(c->h_q.p, c->q_out.p, sizeof(int) * Q, cudaMemcpyDeviceToHost, c->stream));
   MOIP_CUDA(cudaMemcpyAsync(c->h_q.p + Q, c->q_which.p, sizeof(int) * Q, cudaMemcpyDeviceToHost, c->stream));
+  c->kmark(9);
   MOIP_CUDA(cudaStreamSynchronize(c->stream));
+  if (c->ktiming) { c->ktimes.k3_ms += c->kspan(8, 9); c->ktimes.scans += 1; }
   std::memcpy(first_match, c->h_q.p, sizeof(int) * Q);
   if (which) std::memcpy(which, c->h_q.p + Q, sizeof(int) * Q);
   if (rec_out)
@@ -504,6 +550,12 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     for (int j = 0; j < n; ++j) v += M.ci[(size_t)cost * n + j] * (long long)(*inc_x_in)[j];
     have_inc = true; inc_val = (long long)sgn * v; inc_x = *inc_x_in;
   }
+  if (use_points) {     // MIP start: the best point on record that satisfies the objective bounds (and beats the given start)
+    long long v = 0;
+    if (model->points.best(cost, (long long)sgn, olo.data(), ohi.data(), have_inc ? inc_val : LLONG_MAX, inc_x, v)) {
+      have_inc = true; inc_val = v; start_hits += 1;
+    }
+  }
   // batch geometry
   int Bmax = bb_batch > 0 ? bb_batch : num_sms * (dm.n <= 64 ? 16 : 4);
   if (ensure_pool(std::max(256, 4 * Bmax))) return MOIP_ERR_CUDA;
@@ -618,7 +670,9 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       const double cut = have_inc ? (double)inc_val : HUGE_VAL;
       std::memcpy(hi + LI.cutoff, &cut, sizeof(double));
       std::memcpy(hi + LI.rhs, srhs, sizeof(double) * k);
+      kmark(0);
       MOIP_CUDA(cudaMemcpyAsync(r_in.p, hi, LI.end, cudaMemcpyHostToDevice, stream));
+      kmark(1);
     }
     const int* d_ids = reinterpret_cast<const int*>(r_in.p + LI.ids);
     const int* d_cost = reinterpret_cast<const int*>(r_in.p + LI.cost);
@@ -637,6 +691,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     long long* d_cobj = reinterpret_cast<long long*>(r_out.p + LO.cobj);
     unsigned char* d_cfeas = r_out.p + LO.cfeas;
     if (launch_k2_propagate(dm, pool, B, d_ids, d_olo, d_ohi, 16, d_flag, d_leaf, stream)) return MOIP_ERR_CUDA;
+    kmark(2);
     LpBatch b{};
     b.B = B; b.rhs = d_rhs; b.lb = pool.lb; b.ub = pool.ub; b.slot = d_ids; b.rc_fix = have_inc ? 1 : 0;
     b.warm_x = pool.wx; b.warm_y = pool.wy; b.out_x = pool.wx; b.out_y = pool.wy;   // iterate returns to the node's slot
@@ -646,13 +701,24 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     b.cost_idx = d_cost;           // one shared cost index (cost_stride = 0)
     if (attach_k1_scratch(b)) return MOIP_ERR_CUDA;
     if (launch_k1_any(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
-    if (launch_k4_round(dm, B, d_ids, pool.wx, pool.lb, pool.ub, r_xr.p, d_cobj, d_cfeas, d_ff, stream)) return MOIP_ERR_CUDA;
+    kmark(3);
+    if (launch_k4_round(dm, B, d_ids, pool.wx, pool.lb, pool.ub, r_xr.p, d_cobj, d_cfeas, d_ff, d_flag, stream)) return MOIP_ERR_CUDA;
     stats.kernel_launches += 3;
+    kmark(4);
     unsigned char* H = h_round.p;
     MOIP_CUDA(cudaMemcpyAsync(H, r_out.p, LO.end, cudaMemcpyDeviceToHost, stream));
+    kmark(5);
     const double tp1 = prof ? now_s() : 0.0;
     MOIP_CUDA(cudaStreamSynchronize(stream));
     const double tp2 = prof ? now_s() : 0.0;
+    if (ktiming) {
+      ktimes.copy_ms += kspan(0, 1) + kspan(4, 5);
+      ktimes.k2_ms += kspan(1, 2) + (kev_branch_pending ? kspan(6, 7) : 0.0);
+      ktimes.k1_ms += kspan(2, 3);
+      ktimes.k4_ms += kspan(3, 4);
+      ktimes.rounds += 1;
+      kev_branch_pending = false;
+    }
     const int* flag = (const int*)(H + LO.flag);
     const int* status = (const int*)(H + LO.status);
     const int* iters = (const int*)(H + LO.iters);
@@ -766,7 +832,10 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
       if (r_ops.ensure(ops.size()) || h_ops.ensure(ops.size())) return MOIP_ERR_CUDA;
       std::memcpy(h_ops.p, ops.data(), sizeof(BranchOp) * ops.size());     // pinned; rewritten only after the next round's sync
       MOIP_CUDA(cudaMemcpyAsync(r_ops.p, h_ops.p, sizeof(BranchOp) * ops.size(), cudaMemcpyHostToDevice, stream));
+      kmark(6);
       if (launch_k2_branch(dm, pool, (int)ops.size(), r_ops.p, stream)) return MOIP_ERR_CUDA;
+      kmark(7);
+      kev_branch_pending = ktiming;
       stats.kernel_launches += 1;
     }
     for (int s : to_free) free_slots.push_back(s);
@@ -782,6 +851,16 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     out.status = MOIP_MIP_OPTIMAL;
     out.obj = (long long)sgn * inc_val;
     out.x = inc_x;
+    if (use_points) {
+      long long ov[MOIP_MAX_OBJ] = {0, 0, 0, 0};
+      for (int o = 0; o < k; ++o) {
+        long long v = 0;
+        const int64_t* co = M.ci.data() + (size_t)o * n;
+        for (int j = 0; j < n; ++j) v += co[j] * (long long)inc_x[j];
+        ov[o] = v;
+      }
+      model->points.add(inc_x.data(), ov);
+    }
   }
   return MOIP_OK;
 }

@@ -1,7 +1,10 @@
 // Host driver state behind the opaque handles of include/moip_b200.h.
 #pragma once
 #include <chrono>
+#include <array>
 #include <mutex>
+#include <set>
+#include <shared_mutex>
 #include <string>
 #include <vector>
 
@@ -9,8 +12,64 @@
 #include "model.h"
 #include "nodepool.h"
 
+namespace moip {
+
+// Feasible integer points met while solving -- the optimiser of every IP any context of this model has solved -- kept as
+// MIP starts for later IPs.  CPLEX keeps the last solution as a start when only right-hand sides change (what the
+// reference gets for free between the CPXmipopt calls of solve(), src/aira.cpp:467-517, and from one subproblem to the
+// next); here a new IP starts from the best stored point that satisfies its objective bounds.  Points are exact facts
+// (verified in int64 before they became incumbents), so starting from one never changes a result, only the node count.
+struct PointStore {
+  static constexpr size_t kMaxBytes = (size_t)256 << 20;
+  std::shared_mutex mu;
+  int n = 0, k = 0;
+  bool narrow = false;                 // every column fits int8 (binaries): 1 byte per column
+  std::vector<long long> obj;          // [P][k]
+  std::vector<int8_t> x8;              // [P][n]
+  std::vector<int> x32;                // [P][n]
+  std::set<std::array<long long, MOIP_MAX_OBJ>> seen;   // one point per objective vector is enough
+  long long hits = 0, queries = 0;
+  void init(int n_, int k_, bool narrow_) { n = n_; k = k_; narrow = narrow_; }
+  size_t size() const { return k ? obj.size() / (size_t)k : 0; }
+  void add(const int* x, const long long* ov) {
+    std::array<long long, MOIP_MAX_OBJ> key{};
+    for (int o = 0; o < k; ++o) key[o] = ov[o];
+    std::unique_lock<std::shared_mutex> lk(mu);
+    if ((size() + 1) * (size_t)n * (narrow ? 1 : 4) > kMaxBytes) return;
+    if (!seen.insert(key).second) return;
+    obj.insert(obj.end(), ov, ov + k);
+    if (narrow) for (int j = 0; j < n; ++j) x8.push_back((int8_t)x[j]);
+    else x32.insert(x32.end(), x, x + n);
+  }
+  // best stored point (smallest sgn * obj[cost]) with olo <= obj <= ohi and value < below (min-form); false = none
+  bool best(int cost, long long sgn, const long long* olo, const long long* ohi, long long below, std::vector<int>& x_out,
+            long long& val_out) {
+    std::shared_lock<std::shared_mutex> lk(mu);
+    const size_t P = size();
+    size_t arg = P;
+    long long bv = below;
+    for (size_t p = 0; p < P; ++p) {
+      const long long* ov = obj.data() + p * k;
+      const long long v = sgn * ov[cost];
+      if (v >= bv) continue;
+      bool ok = true;
+      for (int o = 0; o < k && ok; ++o) ok = ov[o] >= olo[o] && ov[o] <= ohi[o];
+      if (ok) { bv = v; arg = p; }
+    }
+    if (arg == P) return false;
+    x_out.resize(n);
+    if (narrow) for (int j = 0; j < n; ++j) x_out[j] = x8[arg * n + j];
+    else for (int j = 0; j < n; ++j) x_out[j] = x32[arg * n + j];
+    val_out = bv;
+    return true;
+  }
+};
+
+}  // namespace moip
+
 struct moip_model {
   moip::Model M;
+  moip::PointStore points;
 };
 
 namespace moip {
@@ -120,6 +179,15 @@ struct moip_ctx {
   int bb_check = 32;
   int norm_every = 1;
   int bb_levels = 3;           // max tree levels expanded per round while the device is under-filled
+  bool use_points = true;      // start every IP from the best stored feasible point (PointStore); MOIP_POINT_STORE=0 disables
+  long long start_hits = 0;    // IPs that began with a stored point as incumbent
+
+  // CUDA-event split per kernel class (moip_ctx_set_kernel_timing)
+  bool ktiming = false, kev_branch_pending = false;
+  cudaEvent_t kev[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  moip_kernel_times ktimes{};
+  void kmark(int i) { if (ktiming) cudaEventRecord(kev[i], stream); }
+  double kspan(int a, int b) { float ms = 0.f; return cudaEventElapsedTime(&ms, kev[a], kev[b]) == cudaSuccess ? (double)ms : 0.0; }
 
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 

@@ -6,6 +6,7 @@ import os
 import re
 import subprocess
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -216,13 +217,19 @@ class _OracleBackend:
     def get_limit(self, obj, rhs):
         return self.fs.get_limit(obj, rhs)
 
-    def run_strips(self, n_obj, strips, claim):
+    exchange = True            # offer the level's stores to aira.RecordExchange (the cross-rank cache sharing)
+
+    def run_strips(self, n_obj, strips, claim, share=0):
         here, inf = ao.Solutions(self.k), ao.Solutions(self.k)
+        self._stores, self._cursor, self._foreign = (inf, here), [0, 0], set()
+        self.hits_on_foreign = getattr(self, "hits_on_foreign", 0)
 
         def find(ip):
             _, r = inf.find(ip, self.model.sense)
             if r is None:
                 _, r = here.find(ip, self.model.sense)
+            if r is not None and id(r) in self._foreign:
+                self.hits_on_foreign += 1
             return None if r is None else (r.infeasible, r.result)
 
         def insert(ip, res, infeasible):
@@ -235,10 +242,61 @@ class _OracleBackend:
             a, b = strips[t]
             w = self.mb.make_worker(self.k, n_obj=n_obj, split=True, split_start=a, split_stop=b, wid=t)
             self.mb.optimise_with(self.k, self.sense, w, self.fs.lex_solve, find, insert)
-        return [tuple(r.result) for r in here.store if not r.infeasible]
+            if getattr(self, "strip_delay", 0):
+                time.sleep(self.strip_delay)  # lets the exchange thread carry records between the ranks
+        stores, self._stores = self._stores, None
+        return [tuple(r.result) for r in here.store if not r.infeasible and id(r) not in self._foreign]
+
+    # -- the endpoint of aira.RecordExchange (the role moip_pool_export_records / _import_records play on the GPU)
+    def exchange_endpoint(self):
+        return self if self.exchange else None
+
+    def export_records(self, cap):
+        ip, res, infl = [], [], []
+        stores = getattr(self, "_stores", None)
+        if stores:
+            for w, st in enumerate(stores):
+                while self._cursor[w] < len(st.store) and len(infl) < cap:
+                    r = st.store[self._cursor[w]]
+                    self._cursor[w] += 1
+                    if id(r) in self._foreign:
+                        continue
+                    ip.append(list(r.ip)); res.append([0] * self.k if r.infeasible else list(r.result)); infl.append(int(r.infeasible))
+        return np.array(ip, dtype=float).reshape(-1, self.k), np.array(res, dtype=np.int32).reshape(-1, self.k), np.array(infl, dtype=np.int32)
+
+    def import_records(self, ip, res, infl):
+        stores = getattr(self, "_stores", None)
+        if not stores:
+            return
+        for a, b, f in zip(ip, res, infl):
+            st = stores[0] if f else stores[1]
+            st.insert([float(v) for v in a], None if f else [int(v) for v in b], bool(f))
+            self._foreign.add(id(st.store[-1]))
 
     def sequential_front(self):
         return ao.pareto_front(self.model, self.fs)
+
+    def synergistic_local(self, n_workers):
+        """-t N without --split in one process: min(N, k) cooperative workers on host threads (oracle as the solver)"""
+        import threading
+        w = max(1, min(int(n_workers), self.k))
+        infs, sols, lock = ao.Solutions(self.k), [ao.Solutions(self.k) for _ in range(w)], threading.Lock()
+
+        def solve(i, pm, n_obj, rhs):
+            with lock:
+                return self.fs.lex_solve(pm, n_obj, rhs)
+
+        def find(i, ip):
+            _, r = infs.find(ip, self.model.sense)
+            if r is None:
+                _, r = sols[i].find(ip, self.model.sense)
+            return None if r is None else (r.infeasible, r.result)
+
+        def insert(i, ip, res, infeasible):
+            (infs if infeasible else sols[i]).insert(ip, res, infeasible)
+
+        self.mb.coop_optimise_with(self.k, self.sense, w, solve, find, insert)
+        return sorted({tuple(r.result) for s_ in sols for r in s_.store if not r.infeasible}, key=lambda r: tuple(-v for v in r))
 
     def split_strips(self, biggest, smallest, num_threads, split_normal):
         return self.mb.split_strips(self.sense, biggest, smallest, num_threads, split_normal)
@@ -257,14 +315,19 @@ def test_aira_cli_epp_single_process(lib, examples, stem, tmp_path):
     assert parse_out(open(out).read()) == (e["rows"], e["count"])
 
 
-def test_aira_cli_threads_without_split_runs_strips(lib, examples, tmp_path):
-    """-t N without --split (the reference's synergistic mode): same front, computed as N EPP strips."""
+def test_aira_cli_threads_without_split_runs_cooperative_workers(lib, examples, tmp_path, monkeypatch):
+    """-t N without --split (the reference's synergistic mode, src/aira.cpp:277-308): min(N, k) cooperative workers;
+    MOIP_THREADS_AS_STRIPS=1 maps the N workers onto N EPP strips instead.  Same front either way."""
     from moip_aira_b200 import aira
     from oracle.lpformat import parse_out
     e = examples["3AP05"]
     out = str(tmp_path / "o.out")
     assert aira.main(["-p", e["path"], "-o", out, "-t", "4"], backend_factory=_OracleBackend) == 0
     assert parse_out(open(out).read()) == (e["rows"], e["count"])
+    monkeypatch.setenv("MOIP_THREADS_AS_STRIPS", "1")
+    assert aira.main(["-p", e["path"], "-o", out, "-t", "4"], backend_factory=_OracleBackend) == 0
+    assert parse_out(open(out).read()) == (e["rows"], e["count"])
+    monkeypatch.delenv("MOIP_THREADS_AS_STRIPS")
     assert aira.main(["-p", e["path"], "-o", out], backend_factory=_OracleBackend) == 0      # -t 1: sequential generator
     assert parse_out(open(out).read()) == (e["rows"], e["count"])
 
@@ -298,3 +361,58 @@ def test_aira_cli_epp_two_ranks_gloo(lib, examples, stem, threads, tmp_path):
     for p in procs:
         assert p.wait(timeout=300) == 0
     assert parse_out(open(out).read()) == (e["rows"], e["count"])
+
+
+_EXCHANGE_RANK_SCRIPT = r'''
+import json, os, sys
+sys.path.insert(0, {root!r})
+sys.path.insert(0, os.path.join({root!r}, "tests"))
+from moip_aira_b200 import aira
+from test_host import _OracleBackend
+dist = aira.Dist(None)
+be = _OracleBackend({path!r})
+be.strip_delay = 0.05
+stats = []
+front = aira.epp_front(be, dist, {threads}, False, stats)
+json.dump({{"front": front, "stats": stats, "ips": be.ip_count(), "hits_on_foreign": be.hits_on_foreign}},
+          open({out!r} + "." + os.environ["RANK"], "w"))
+import torch.distributed as td
+td.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("stem,world,threads", [("4AP05", 2, 8), ("4KP10", 3, 9), ("3AP05", 2, 6)])
+def test_epp_record_exchange_ranks_gloo(lib, examples, stem, world, threads, tmp_path):
+    """The cross-rank knowledge exchange (aira.RecordExchange): while a level's strips run, every rank all-gathers the
+    cache records it produces; the other ranks' strips may answer their subproblems from them (Solutions::find semantics,
+    reference src/solutions.cpp:11-81, so the front cannot change).  Every rank must end up with the golden front, records
+    must actually have travelled, and each rank reports only the points it found itself."""
+    e = examples[stem]
+    out = str(tmp_path / "x.json")
+    script = tmp_path / "rank.py"
+    script.write_text(_EXCHANGE_RANK_SCRIPT.format(root=ROOT, path=e["path"], out=out, threads=threads))
+    port = 31500 + (os.getpid() % 2000)
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), MOIP_EXCHANGE_PERIOD_MS="2")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env))
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    import json
+    res = [json.load(open(out + "." + str(r))) for r in range(world)]
+    for r in res:
+        assert [list(x) for x in r["front"]] == [list(x) for x in e["rows"]]
+    top = [r["stats"][-1] for r in res]
+    assert sum(t["records_sent"] for t in top) > 0
+    assert sum(t["records_received"] for t in top) == (world - 1) * sum(t["records_sent"] for t in top)
+    assert all(t["exchange_rounds"] == top[0]["exchange_rounds"] for t in top)      # the loop ends in the same round everywhere
+
+
+def test_pool_record_exchange_is_a_noop_between_runs(lib, examples):
+    """moip_pool_export_records / _import_records need no GPU to refuse bad arguments"""
+    import ctypes as C
+    n = C.c_int(-1)
+    assert lib._lib.moip_pool_export_records(None, 0, None, None, None, C.byref(n)) == 1
+    assert lib._lib.moip_pool_import_records(None, 0, None, None, None) == 1
+    assert lib._lib.moip_pool_set_max_workers(None, 1) == 1

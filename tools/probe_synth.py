@@ -23,4 +23,7 @@ for spec in sys.argv[1:]:
           f"iters/lp={s['lp_iterations']/max(1,s['node_lps']):.0f} launches={s['kernel_launches']} "
           f"ms/ip={1e3*dt/max(1,s['ip_solved']):.2f} nodes/ip={s['bb_nodes']/max(1,s['ip_solved']):.1f} "
           f"solver_s={s['solver_seconds']:.2f}", flush=True)
+    if os.environ.get("MOIP_KERNEL_TIMING"):
+        kt = ctx.kernel_times()
+        print("   kernel-class ms (CUDA events, summed over contexts): " + " ".join(f"{a}={v:.0f}" if isinstance(v, float) else f"{a}={v}" for a, v in kt.items()), flush=True)
     ctx.close()
