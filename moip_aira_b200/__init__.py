@@ -31,6 +31,9 @@ if not os.path.exists(LIB_PATH):
     raise ImportError(
         f"{LIB_PATH} is missing: build it with `python -m moip_aira_b200.build` "
         "(nvcc, sm_100a).  There is no fallback implementation.")
+# one hardware work queue per worker stream (see csrc/solver.cu, WorkQueueEnv): must be in the environment before the
+# process creates its CUDA context, i.e. before torch touches the device
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 _lib = C.CDLL(LIB_PATH)
 
 

@@ -12,7 +12,7 @@ With --split the EPP strips of every level (src/aira.cpp:1886-1990) are sharded 
 job (one rank per GPU, `torchrun --nproc-per-node G`): the ranks draw strips from one job-wide counter, all-gather the
 cache records they produce while they solve (every strip of the job can reuse every other strip's relaxations, like
 the reference's threads share `here` / `infeasibles`, src/aira.cpp:1918-1933) and all-gather the points found between
-levels; inside a rank the strips run concurrently on a pool of solver contexts (MOIP_WORKERS host threads, default 12)
+levels; inside a rank the strips run concurrently on a pool of solver contexts (MOIP_WORKERS host threads, default 16)
 that share the GPU.  On this backend --split is the faster mode for assignment-type models (profiles/r02_fronts.md).
 """
 from __future__ import annotations
@@ -178,7 +178,7 @@ class GpuBackend:
         self.problem = mb.Problem(path)
         self.k = self.problem.objcnt
         self.sense = self.problem.objsen
-        self.workers = max(1, int(os.environ.get("MOIP_WORKERS", "12")) if workers is None else int(workers))
+        self.workers = max(1, int(os.environ.get("MOIP_WORKERS", "16")) if workers is None else int(workers))
         self._ctx = None
         self._pool = None
 
@@ -219,7 +219,8 @@ class GpuBackend:
         try:
             return pool.synergistic_front(w)
         finally:
-            self._coop_ips = pool.stats()["ip_solved"]
+            st = pool.stats()
+            self._coop_stats = {f: self._coop_stats.get(f, 0) + v for f, v in st.items()} if getattr(self, "_coop_stats", None) else st
             pool.close()
 
     def coop_worker(self, perm, limits):
@@ -236,13 +237,17 @@ class GpuBackend:
     def split_strips(self, biggest, smallest, num_threads, split_normal):
         return self.mb.split_strips(self.sense, biggest, smallest, num_threads, split_normal)
 
+    def stats(self):
+        """counters summed over everything this backend has run (sequential context, strip pool, cooperative pools)"""
+        tot = {}
+        for st in ([self._ctx.stats()] if self._ctx is not None else []) + ([self._pool.stats()] if self._pool is not None else []) + \
+                ([self._coop_stats] if getattr(self, "_coop_stats", None) else []):
+            for f, v in st.items():
+                tot[f] = tot.get(f, 0) + v
+        return tot
+
     def ip_count(self):
-        n = 0
-        if self._ctx is not None:
-            n += self._ctx.stats()["ip_solved"]
-        if self._pool is not None:
-            n += self._pool.stats()["ip_solved"]
-        return n + getattr(self, "_coop_ips", 0)
+        return self.stats().get("ip_solved", 0)
 
 
 def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list | None = None):
@@ -375,11 +380,15 @@ def main(argv=None, backend_factory=None):
     if backend_factory is None:
         import torch
         dev = None
-        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            torch.cuda.set_device(local_rank)
-            dev = torch.device("cuda", local_rank)
+        # one rank per GPU over NCCL; MOIP_DIST_BACKEND=gloo keeps the collectives on the host (several ranks sharing a
+        # GPU, e.g. the 2-rank GPU test on a one-GPU box -- NCCL refuses two ranks on one device)
+        gloo = os.environ.get("MOIP_DIST_BACKEND", "nccl") == "gloo"
+        gpu = local_rank % max(1, torch.cuda.device_count()) if gloo else local_rank
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not gloo:
+            torch.cuda.set_device(gpu)
+            dev = torch.device("cuda", gpu)
         dist = Dist(dev)
-        be = GpuBackend(args.lp, device=local_rank)
+        be = GpuBackend(args.lp, device=gpu)
     else:
         dist = Dist(None)
         be = backend_factory(args.lp)

@@ -86,6 +86,19 @@ struct LpBatch {
   double* scratch;            // generic kernel, large models: per-CTA iterate storage in HBM (nullptr = shared memory)
   size_t scratch_stride;      // doubles per CTA (k1_scratch_stride)
   int scratch_slots;          // CTAs the scratch has room for
+  // Fused B&B round (register-resident K1 only, `slot` set): the CTA that pulls a node first propagates it (K2,
+  // k2_propagate.cuh) and, once its LP is solved, rounds the LP point three ways and verifies the candidates exactly
+  // (what k4_round_verify_kernel does) -- one launch per round instead of three, the node's bounds read once.
+  int fused;                  // 0 = plain LP batch (the f_* fields are ignored)
+  const long long* f_obj_lo;  // [k] integer limits of the objective rows for the propagation (incl. the incumbent cut-off)
+  const long long* f_obj_hi;
+  int f_max_rounds;
+  int* f_flag;                // [B] out: 0 open / 1 infeasible / 2 leaf
+  long long* f_leaf_obj;      // [B][k] exact objective values of leaves
+  int* f_xr;                  // [B][3][n] rounded candidates (nearest / down / up, clipped to the node's box)
+  long long* f_cand_obj;      // [B][3][k]
+  unsigned char* f_cand_feas; // [B][3] structural rows satisfied
+  int* f_first_free;          // [B][3] first unfixed column, its lb, ub
 };
 
 struct LpParams {

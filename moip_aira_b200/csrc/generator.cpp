@@ -524,6 +524,7 @@ struct moip_pool {
   moip_cache* run_inf = nullptr;
   size_t exp_cursor[2] = {0, 0};
   int64_t exported = 0, imported = 0;
+  cudaStream_t xstream = nullptr;            // imported records go to the device on this stream (created on first use)
 };
 
 extern "C" int moip_pool_create(moip_model* m, int device, int workers, moip_pool** out) {
@@ -551,6 +552,7 @@ extern "C" void moip_pool_destroy(moip_pool* p) {
   if (!p) return;
   for (moip_ctx* c : p->ctx) moip_ctx_destroy(c);
   cudaSetDevice(p->device);
+  if (p->xstream) cudaStreamDestroy(p->xstream);
   for (cudaStream_t st : p->streams) cudaStreamDestroy(st);
   delete p;
 }
@@ -599,14 +601,28 @@ extern "C" int moip_pool_import_records(moip_pool* p, int n, const double* ip, c
   std::lock_guard<std::mutex> rl(p->run_mu);
   if (!p->run_here || !p->run_inf) return MOIP_OK;
   const int k = p->run_here->k;
-  for (int i = 0; i < n; ++i) {
-    CacheRecord r{};
-    for (int j = 0; j < k; ++j) { r.ip[j] = ip[(size_t)i * k + j]; r.result[j] = infeasible[i] ? 0 : result[(size_t)i * k + j]; }
-    r.infeasible = infeasible[i] ? 1 : 0;
-    r.pad[0] = 1;
-    moip_cache* s = r.infeasible ? p->run_inf : p->run_here;
+  if (!p->xstream) {
+    if (cudaSetDevice(p->device) != cudaSuccess || cudaStreamCreateWithFlags(&p->xstream, cudaStreamNonBlocking) != cudaSuccess) {
+      p->xstream = nullptr;
+      return MOIP_ERR_CUDA;
+    }
+  }
+  // the batch goes to the device right here, on the exchange's own stream: the workers' scans then find it in place
+  // instead of each paying for an upload under the store's lock
+  for (int w = 0; w < 2; ++w) {
+    moip_cache* s = w ? p->run_here : p->run_inf;
     std::lock_guard<std::mutex> lk(s->mu);
-    s->host.push_back(r);
+    bool any = false;
+    for (int i = 0; i < n; ++i) {
+      if ((infeasible[i] != 0) != (w == 0)) continue;
+      CacheRecord r{};
+      for (int j = 0; j < k; ++j) { r.ip[j] = ip[(size_t)i * k + j]; r.result[j] = infeasible[i] ? 0 : result[(size_t)i * k + j]; }
+      r.infeasible = infeasible[i] ? 1 : 0;
+      r.pad[0] = 1;
+      s->host.push_back(r);
+      any = true;
+    }
+    if (any && s->sync_to_device(p->xstream)) return MOIP_ERR_CUDA;
   }
   p->imported += n;
   return MOIP_OK;

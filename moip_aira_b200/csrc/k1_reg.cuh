@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "device.h"
+#include "k2_propagate.cuh"
 
 namespace moip {
 namespace k1reg {
@@ -147,7 +148,9 @@ constexpr int kProdBase = kYshBytes;       // prod[msS*RWP + 2] products S_ij * 
 constexpr int kDL = 16;                    // lanes that add up one dense row / one norm
 enum { COLD_BEST_LB = 0, COLD_POBJ, COLD_DOBJ, COLD_OBJ_UPPER, COLD_KKT_BINV, COLD_W, COLD_R0SQ, COLD_RPREV, COLD_N = 8 };
 
-template <int NT, int CPT, int KD, int ELLW, int MINB>
+// FUSED: the B&B instantiation (LpBatch::fused): K2 propagation in front of the LP, K4 rounding/verification behind it.
+// The plain instantiation (batch API, bench `value`) carries none of that code, so its iteration loop keeps its registers.
+template <int NT, int CPT, int KD, int ELLW, int MINB, bool FUSED>
 __global__ void __launch_bounds__(NT, MINB)
 k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lpr_log2) {
   constexpr int NW = NT / 32;
@@ -168,6 +171,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
   double* xts = reinterpret_cast<double*>(lu + NT * CPT);    // [CPT][NT] thread-private PDHG point xt
   double* xas = xts + NT * CPT;                              // [CPT][NT] thread-private Halpern anchor
   double* part = xas + NT * CPT;                             // [NV][NT]  per-thread partial sums of the dense rows / norms
+  __shared__ int s_prop[FUSED ? 4 : 1];                      // flags of the fused propagation
   const int tid = threadIdx.x, lane = tid & 31;
   const int LPR = 1 << lpr_log2;
   // ---- roles in the row phase: LPR lanes per short structural row from thread 0 up, one half-warp per dense
@@ -255,13 +259,24 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
     __syncthreads();
     const int node = s_node[0];
     if (node >= b.B) break;
-    if (b.skip && b.skip[node]) {
+    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)node;   // row of the node's arrays
+    if (FUSED) {
+      // ---- fused round, part 1: K2 propagation of this node (xts|xas hold the 4n ints, part the per-warp partial sums)
+      const int f = k2::propagate_node<NT>(dm, b.lb + srow * n, b.ub + srow * n, b.f_obj_lo, b.f_obj_hi, b.f_max_rounds,
+                                           reinterpret_cast<int*>(xts), reinterpret_cast<long long*>(part), s_prop,
+                                           b.f_leaf_obj + (size_t)node * k);
+      if (tid == 0) b.f_flag[node] = f;
+      if (f != 0) {                                           // infeasible or leaf: nothing to solve
+        if (tid == 0) { b.status[node] = -1; b.iters[node] = 0; }
+        __syncthreads();
+        continue;
+      }
+    } else if (b.skip && b.skip[node]) {
       if (tid == 0) { b.status[node] = -1; b.iters[node] = 0; }
       __syncthreads();
       continue;
     }
     // ---------------------------------------------------------------- node load
-    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)node;   // row of the node's arrays
     const int cost = b.cost_idx[(size_t)node * b.cost_stride];
     const double* nrhs = b.rhs + (size_t)node * b.rhs_stride;
     const double inv_dr_cost = 1.0 / dm.dr_k[msS + cost];
@@ -602,6 +617,86 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
         if (r == 0) c0 = pick; else c1 = pick;
       }
     }
+    if (FUSED) {
+      // ---- fused round, part 2: round the LP point three ways (nearest / down / up, clipped to the node's box) and
+      // verify each candidate exactly in int64 -- objective values by a block reduction, structural rows a thread per row
+      // on the candidates staged in shared memory (xts|xas are free: xo holds the point)
+      __syncthreads();
+      int* xr_s = reinterpret_cast<int*>(xts);                // [3][n]
+      long long co[3][MOIP_MAX_OBJ];
+#pragma unroll
+      for (int md = 0; md < 3; ++md)
+#pragma unroll
+        for (int o = 0; o < MOIP_MAX_OBJ; ++o) co[md][o] = 0;
+      int ff = INT_MAX;                                       // first column that is not fixed yet (fallback branching column)
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const int j = tid + c * NT;
+        if (j < n) {
+          const int lj = b.lb[srow * n + j], uj = b.ub[srow * n + j];
+          const double v = xo[c];
+          int r[3] = {(int)llrint(v), (int)floor(v + 1e-6), (int)ceil(v - 1e-6)};
+          if (lj < uj && j < ff) ff = j;
+#pragma unroll
+          for (int md = 0; md < 3; ++md) {
+            r[md] = max(lj, min(uj, r[md]));
+            xr_s[md * n + j] = r[md];
+            b.f_xr[((size_t)node * 3 + md) * n + j] = r[md];
+          }
+#pragma unroll
+          for (int o = 0; o < MOIP_MAX_OBJ; ++o)
+            if (o < k) {
+              const long long cj = dm.ci[(size_t)o * n + j];
+#pragma unroll
+              for (int md = 0; md < 3; ++md) co[md][o] += cj * (long long)r[md];
+            }
+        }
+      }
+      constexpr int RS = 3 * MOIP_MAX_OBJ + 1;                // per-warp partial results: 3 x 4 objective sums + first free column
+      long long* red = reinterpret_cast<long long*>(part);
+#pragma unroll
+      for (int md = 0; md < 3; ++md)
+#pragma unroll
+        for (int o = 0; o < MOIP_MAX_OBJ; ++o) {
+          const long long t = k2::wsum_ll(co[md][o]);
+          if (lane == 0) red[(tid >> 5) * RS + md * MOIP_MAX_OBJ + o] = t;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ff = min(ff, __shfl_xor_sync(0xffffffffu, ff, o));
+      if (lane == 0) red[(tid >> 5) * RS + 3 * MOIP_MAX_OBJ] = ff;
+      __syncthreads();                                        // candidates and partial results visible
+      int bad0 = 0, bad1 = 0, bad2 = 0;
+      for (int i = tid; i < dm.ms; i += NT) {
+        long long a0 = 0, a1 = 0, a2 = 0;
+        for (int e = dm.s_ptr[i]; e < dm.s_ptr[i + 1]; ++e) {
+          const int col = dm.s_col[e];
+          const long long av = dm.ai_val[e];
+          a0 += av * (long long)xr_s[col]; a1 += av * (long long)xr_s[n + col]; a2 += av * (long long)xr_s[2 * n + col];
+        }
+        const long long lo = dm.ri_lo[i], hi = dm.ri_hi[i];
+        bad0 |= (a0 < lo || a0 > hi); bad1 |= (a1 < lo || a1 > hi); bad2 |= (a2 < lo || a2 > hi);
+      }
+      bad0 = __syncthreads_or(bad0); bad1 = __syncthreads_or(bad1); bad2 = __syncthreads_or(bad2);
+      if (tid < 3 * k) {
+        const int md = tid / k, o = tid - md * k;
+        long long t = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) t += red[w * RS + md * MOIP_MAX_OBJ + o];
+        b.f_cand_obj[((size_t)node * 3 + md) * k + o] = t;
+      }
+      if (tid == 0) {
+        b.f_cand_feas[(size_t)node * 3] = bad0 ? 0 : 1;
+        b.f_cand_feas[(size_t)node * 3 + 1] = bad1 ? 0 : 1;
+        b.f_cand_feas[(size_t)node * 3 + 2] = bad2 ? 0 : 1;
+        long long fm = INT_MAX;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) fm = min(fm, red[w * RS + 3 * MOIP_MAX_OBJ]);
+        const int f1 = (int)fm;
+        b.f_first_free[(size_t)node * 3] = f1 == INT_MAX ? -1 : f1;
+        b.f_first_free[(size_t)node * 3 + 1] = f1 == INT_MAX ? 0 : b.lb[srow * n + f1];
+        b.f_first_free[(size_t)node * 3 + 2] = f1 == INT_MAX ? 0 : b.ub[srow * n + f1];
+      }
+    }
     if (tid == 0) {
       b.primal_obj[node] = pobj;
       b.dual_bound[node] = best_lb;
@@ -617,9 +712,9 @@ inline int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-template <int NT, int CPT, int KD, int ELLW, int MINB>
-int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
-  auto kern = k1_reg_kernel<NT, CPT, KD, ELLW, MINB>;
+template <int NT, int CPT, int KD, int ELLW, int MINB, bool FUSED>
+int launch_reg_f(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
+  auto kern = k1_reg_kernel<NT, CPT, KD, ELLW, MINB, FUSED>;
   const size_t prod_len = ((size_t)dm.msS * dm.RWP + 2 + 1) & ~(size_t)1;
   const size_t smem = kYshBytes + sizeof(double) * (prod_len + 256 + 8 + COLD_N + 2 + (size_t)16 * (NT / 32) + 2 +
                                                     (size_t)4 * NT * CPT + (size_t)(KD + 2) * NT);
@@ -652,6 +747,15 @@ int launch_reg(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cu
   kern<<<(unsigned)grid, NT, smem, st>>>(dm, b, p, dm.reg_lpr_log2);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
+}
+
+template <int NT, int CPT, int KD, int ELLW, int MINB>
+int launch_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
+  if (b.fused) {
+    if (!b.slot) return MOIP_ERR_ARG;
+    return launch_reg_f<NT, CPT, KD, ELLW, MINB, true>(dm, b, p, num_sms, st);
+  }
+  return launch_reg_f<NT, CPT, KD, ELLW, MINB, false>(dm, b, p, num_sms, st);
 }
 
 // shape dispatch for one KD (one translation unit per KD keeps the build parallel)

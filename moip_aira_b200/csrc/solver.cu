@@ -36,6 +36,14 @@ int moip::aux_grid_cap() {
 
 namespace {
 
+// Worker contexts put one stream each on the device; with the default of 8 hardware work queues, streams share a queue
+// and a small copy of one worker waits behind another worker's K1 launch (measured: 109 us of copy time per B&B round
+// with 12 workers, 28 us with 32 queues).  The driver reads the variable when it creates the device context, so it is
+// set when the library is loaded -- an explicit setting by the user wins.
+struct WorkQueueEnv {
+  WorkQueueEnv() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_work_queue_env;
+
 template <class T>
 int upload(moip_ctx* c, const std::vector<T>& v, const T** out) {
   T* p = nullptr;
@@ -139,6 +147,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->norm_every = env_int("MOIP_NORM_EVERY", 16);
   c->bb_levels = env_int("MOIP_BB_LEVELS", 3);
   c->use_points = env_int("MOIP_POINT_STORE", 1) != 0;
+  c->use_fused = env_int("MOIP_FUSED_ROUND", 1) != 0;
   {
     std::unique_lock<std::shared_mutex> lk(m->points.mu);
     if (m->points.n == 0) {
@@ -173,6 +182,13 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
     std::fprintf(stderr, "moip_b200: %.0f B&B rounds (%.1f nodes each), node-LP cap %d (%.0f %% of the LPs hit it): enqueue %.1f us, wait for the device %.1f us, host %.1f us per round\n",
                  c->prof_t[3], c->prof_t[4] / c->prof_t[3], c->bb_max_iter > 0 ? c->bb_max_iter : c->lp_cap_dyn, 100.0 * c->prof_t[6] / std::max(1.0, c->prof_t[5]), 1e6 * c->prof_t[0] / c->prof_t[3], 1e6 * c->prof_t[1] / c->prof_t[3],
                  1e6 * c->prof_t[2] / c->prof_t[3]);
+  if (c->prof_t[3] > 0)
+    for (int sg = 0; sg <= MOIP_MAX_OBJ; ++sg)
+      if (c->stage_ips[sg])
+        std::fprintf(stderr, "moip_b200:   stage %d%s: %lld IPs, %.1f nodes, %.1f node LPs, %.2f rounds per IP; %.0f %% of them done after the root round; %lld started from a stored point\n",
+                     sg, sg == MOIP_MAX_OBJ ? " (get_limit / mip_solve)" : "", c->stage_ips[sg], (double)c->stage_nodes[sg] / c->stage_ips[sg],
+                     (double)c->stage_lps[sg] / c->stage_ips[sg], (double)c->stage_rounds[sg] / c->stage_ips[sg],
+                     100.0 * c->stage_root_solved[sg] / c->stage_ips[sg], sg == 0 ? c->start_hits : 0LL);
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->kev) if (e) cudaEventDestroy(e);
@@ -327,11 +343,20 @@ extern "C" int moip_lp_batch_solve(moip_ctx* c, int B, const int* cost_idx, cons
 int moip_cache::sync_to_device(cudaStream_t st) {
   if (synced == host.size()) return MOIP_OK;
   MOIP_CUDA(cudaSetDevice(device));
-  if (dev.ensure(host.size(), true, st)) return MOIP_ERR_CUDA;
+  if (host.size() > dev.cap) {
+    // grow: a new array, refilled from the host mirror.  The old one is only retired -- a scan another worker launched
+    // from its snapshot may still be reading it -- and freed with the store.
+    size_t nc = dev.cap ? dev.cap * 2 : 1024;
+    while (nc < host.size()) nc *= 2;
+    CacheRecord* q = nullptr;
+    MOIP_CUDA(cudaMalloc(&q, nc * sizeof(CacheRecord)));
+    if (dev.p) retired.push_back(dev.p);
+    dev.p = q; dev.cap = nc;
+    synced = 0;
+  }
   MOIP_CUDA(cudaMemcpyAsync(dev.p + synced, host.data() + synced, sizeof(CacheRecord) * (host.size() - synced),
                             cudaMemcpyHostToDevice, st));
-  // host.data() may be reallocated by a later insert: finish the copy before returning.  `st` is the calling
-  // worker's own stream (a store shared by a pool must not wait for another worker's B&B round).
+  // the records must have landed before `synced` is published: scans of OTHER workers run on other streams
   MOIP_CUDA(cudaStreamSynchronize(st));
   synced = host.size();
   return MOIP_OK;
@@ -353,6 +378,7 @@ extern "C" void moip_cache_destroy(moip_cache* s) {
   if (!s) return;
   cudaSetDevice(s->device);
   s->dev.release();
+  for (CacheRecord* q : s->retired) cudaFree(q);
   delete s;
 }
 extern "C" int moip_cache_insert(moip_cache* s, const double* ip, const int* result, int infeasible) {
@@ -370,22 +396,30 @@ extern "C" int moip_cache_size(const moip_cache* s) {
   return (int)s->host.size();
 }
 
-// shared by the public batch call and the generator (two stores, one launch, one sync)
+// shared by the public batch call and the generator (two stores, one launch, one sync).  A store's lock is held only
+// while its new records go to the device and the {array, size} snapshot is taken -- not across the scan: the stores of
+// an EPP level are shared by every worker of the pool (src/aira.cpp:1918-1933), and a 4-objective knapsack front asks
+// them 10x more often than it solves.  Records are append-only while workers run, so a snapshot stays valid.
 int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double* ip, int sense, int* first_match, int* which,
                 CacheRecord* rec_out) {
   MOIP_CUDA(cudaSetDevice(c->device));
   const int k = c->dm.k;
-  // both stores stay locked from the device sync to the read-back: another worker's insert may move the host array
-  std::unique_lock<std::mutex> l0, l1;
-  if (s0) l0 = std::unique_lock<std::mutex>(s0->mu);
-  if (s1 && s1 != s0) l1 = std::unique_lock<std::mutex>(s1->mu);
-  if (s0 && s0->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
-  if (s1 && s1->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
+  DevCache e{}; e.k = k; e.size = 0; e.rec = nullptr;
+  DevCache v0 = e, v1 = e;
+  if (s0) {
+    std::lock_guard<std::mutex> lk(s0->mu);
+    if (s0->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
+    v0 = s0->view();
+  }
+  if (s1 && s1 != s0) {
+    std::lock_guard<std::mutex> lk(s1->mu);
+    if (s1->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
+    v1 = s1->view();
+  }
   if (c->q_ip.ensure((size_t)Q * k) || c->q_out.ensure(Q) || c->q_which.ensure(Q) || c->h_q.ensure((size_t)2 * Q)) return MOIP_ERR_CUDA;
   c->kmark(8);
   MOIP_CUDA(cudaMemcpyAsync(c->q_ip.p, ip, sizeof(double) * Q * k, cudaMemcpyHostToDevice, c->stream));
-  DevCache e{}; e.k = k; e.size = 0; e.rec = nullptr;
-  int rc = launch_k3(s0 ? s0->view() : e, s1 ? s1->view() : e, Q, c->q_ip.p, sense, c->q_out.p, c->q_which.p, c->stream);
+  int rc = launch_k3(v0, v1, Q, c->q_ip.p, sense, c->q_out.p, c->q_which.p, c->stream);
   if (rc) return rc;
   c->stats.kernel_launches += 1;
   c->stats.cache_queries += Q;
@@ -398,7 +432,11 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
   if (which) std::memcpy(which, c->h_q.p + Q, sizeof(int) * Q);
   if (rec_out)
     for (int q = 0; q < Q; ++q)
-      if (first_match[q] >= 0) rec_out[q] = ((c->h_q.p[Q + q] == 0 ? s0 : s1))->host[first_match[q]];
+      if (first_match[q] >= 0) {
+        moip_cache* s = c->h_q.p[Q + q] == 0 ? s0 : s1;
+        std::lock_guard<std::mutex> lk(s->mu);
+        rec_out[q] = s->host[first_match[q]];
+      }
   return MOIP_OK;
 }
 
@@ -530,6 +568,8 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   const int n = dm.n, k = dm.k, m = dm.m;
   const double sgn = dm.sgn;
   stats.ip_solved += 1;
+  stage_ips[cur_stage] += 1;
+  long long ip_rounds = 0;
   out.status = MOIP_MIP_INFEASIBLE;
   out.x.clear();
   if (M.int_infeasible) return MOIP_OK;
@@ -652,6 +692,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     const int B = (int)batch.size();
     if (B == 0) break;
     stats.bb_nodes += B;
+    stage_nodes[cur_stage] += B; stage_rounds[cur_stage] += 1; ++ip_rounds;
     // ---- device round: propagate -> gather -> LP -> scatter/round -> verify
     std::vector<long long> plo = olo, phi = ohi;
     if (have_inc) {   // incumbent cut-off row on the optimised objective: must be strictly better
@@ -690,20 +731,26 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     long long* d_leaf = reinterpret_cast<long long*>(r_out.p + LO.leaf);
     long long* d_cobj = reinterpret_cast<long long*>(r_out.p + LO.cobj);
     unsigned char* d_cfeas = r_out.p + LO.cfeas;
-    if (launch_k2_propagate(dm, pool, B, d_ids, d_olo, d_ohi, 16, d_flag, d_leaf, stream)) return MOIP_ERR_CUDA;
+    // register-resident K1: propagate -> LP -> round/verify of a node happen in ONE CTA of one launch (fused round)
+    const bool fused = dm.reg_ok && use_fused;
+    if (!fused && launch_k2_propagate(dm, pool, B, d_ids, d_olo, d_ohi, 16, d_flag, d_leaf, stream)) return MOIP_ERR_CUDA;
     kmark(2);
     LpBatch b{};
     b.B = B; b.rhs = d_rhs; b.lb = pool.lb; b.ub = pool.ub; b.slot = d_ids; b.rc_fix = have_inc ? 1 : 0;
+    if (fused) {
+      b.fused = 1; b.f_obj_lo = d_olo; b.f_obj_hi = d_ohi; b.f_max_rounds = 16; b.f_flag = d_flag; b.f_leaf_obj = d_leaf;
+      b.f_xr = r_xr.p; b.f_cand_obj = d_cobj; b.f_cand_feas = d_cfeas; b.f_first_free = d_ff;
+    }
     b.warm_x = pool.wx; b.warm_y = pool.wy; b.out_x = pool.wx; b.out_y = pool.wy;   // iterate returns to the node's slot
     b.primal_obj = r_pobj.p; b.dual_bound = d_dbound; b.status = d_status; b.iters = d_iters;
-    b.branch_var = d_branch; b.branch_val = d_bval; b.skip = d_flag;
+    b.branch_var = d_branch; b.branch_val = d_bval; b.skip = fused ? nullptr : d_flag;
     b.cost_stride = 0; b.rhs_stride = 0; b.cutoff = d_cutoff; b.work_counter = r_counter.p;
     b.cost_idx = d_cost;           // one shared cost index (cost_stride = 0)
     if (attach_k1_scratch(b)) return MOIP_ERR_CUDA;
     if (launch_k1_any(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
     kmark(3);
-    if (launch_k4_round(dm, B, d_ids, pool.wx, pool.lb, pool.ub, r_xr.p, d_cobj, d_cfeas, d_ff, d_flag, stream)) return MOIP_ERR_CUDA;
-    stats.kernel_launches += 3;
+    if (!fused && launch_k4_round(dm, B, d_ids, pool.wx, pool.lb, pool.ub, r_xr.p, d_cobj, d_cfeas, d_ff, d_flag, stream)) return MOIP_ERR_CUDA;
+    stats.kernel_launches += fused ? 1 : 3;
     kmark(4);
     unsigned char* H = h_round.p;
     MOIP_CUDA(cudaMemcpyAsync(H, r_out.p, LO.end, cudaMemcpyDeviceToHost, stream));
@@ -743,6 +790,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
         if (v < best_val) { best_val = v; best_src = i * 3; best_is_leaf = true; }
       } else if (flag[i] == 0) {
         stats.node_lps += 1;
+        stage_lps[cur_stage] += 1;
         stats.lp_iterations += iters[i];
         for (int c3 = 0; c3 < 3; ++c3) {
           const size_t w3 = (size_t)i * 3 + c3;
@@ -842,6 +890,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     if (prof) { const double tp3 = now_s(); prof_t[0] += tp1 - tp0; prof_t[1] += tp2 - tp1; prof_t[2] += tp3 - tp2; prof_t[3] += 1; prof_t[4] += B; }
   }
   for (auto& nd : open) free_slots.push_back(nd.slot);
+  if (ip_rounds <= 1) stage_root_solved[cur_stage] += 1;
   if (have_inc) {
     if (inc_on_device) {
       inc_x.resize(n);
@@ -876,7 +925,9 @@ int moip_ctx::lex_solve(const int* perm, int n_obj, const double* rhs, int* resu
   for (int jp = 0; jp < n_obj; ++jp) {               // :467
     const int j = perm[jp];
     IpResult r;
+    cur_stage = jp;
     int rc = solve_ip(j, srhs.data(), x.empty() ? nullptr : &x, r);
+    cur_stage = MOIP_MAX_OBJ;
     if (rc) return rc;
     st = r.status;
     if (st == MOIP_MIP_INFEASIBLE) break;            // :489-492

@@ -126,10 +126,11 @@ struct moip_cache {
   int k = 0;
   std::vector<moip::CacheRecord> host;   // insertion order
   moip::DBuf<moip::CacheRecord> dev;
+  std::vector<moip::CacheRecord*> retired;   // device arrays outgrown while scans of other workers may still read them: freed with the store
   size_t synced = 0;                     // records [0, synced) are on the device
   std::mutex mu;                         // the stores are shared by the worker threads of a pool (src/solutions.h:41-44)
-  int sync_to_device(cudaStream_t st);
-  moip::DevCache view() const;
+  int sync_to_device(cudaStream_t st);   // caller holds mu
+  moip::DevCache view() const;           // caller holds mu; the snapshot stays valid after the lock is released
 };
 
 struct moip_ctx {
@@ -179,6 +180,7 @@ struct moip_ctx {
   int bb_check = 32;
   int norm_every = 1;
   int bb_levels = 3;           // max tree levels expanded per round while the device is under-filled
+  bool use_fused = true;       // register-resident K1: one fused propagate -> LP -> round/verify launch per round (MOIP_FUSED_ROUND=0: three kernels)
   bool use_points = true;      // start every IP from the best stored feasible point (PointStore); MOIP_POINT_STORE=0 disables
   long long start_hits = 0;    // IPs that began with a stored point as incumbent
 
@@ -189,6 +191,10 @@ struct moip_ctx {
   void kmark(int i) { if (ktiming) cudaEventRecord(kev[i], stream); }
   double kspan(int a, int b) { float ms = 0.f; return cudaEventElapsedTime(&ms, kev[a], kev[b]) == cudaSuccess ? (double)ms : 0.0; }
 
+  long long stage_ips[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0}, stage_nodes[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0},
+            stage_lps[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0}, stage_rounds[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0},
+            stage_root_solved[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0};   // per stage of the lexicographic chain (MOIP_PROFILE_ROUNDS)
+  int cur_stage = MOIP_MAX_OBJ;       // stage of the IP being solved (MOIP_MAX_OBJ = outside lex_solve)
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
   moip::DBuf<double> k1_scratch;   // streaming mode of the generic K1 kernel (models too large for shared memory)
