@@ -204,7 +204,11 @@ def main():
     ap.add_argument("--no-fronts", action="store_true")
     ap.add_argument("--front-instances", default="ap3_30_1,kp4_40_1",
                     help="synthetic instances (tests/golden) whose Pareto fronts are timed with the EPP strips sharded over the ranks")
-    ap.add_argument("--front-strips-per-gpu", type=int, default=0, help="EPP strips per GPU (0 = 2 per solver context)")
+    ap.add_argument("--front-strips-per-gpu", type=int, default=0,
+                    help="EPP strips per GPU (0 = one per solver context for 3-objective instances, a quarter of that for 4 "
+                         "objectives, where every strip starts with a 3-objective front of its own; idle workers cut busy strips)")
+    ap.add_argument("--front-budget-s", type=float, default=600.0,
+                    help="wall-clock budget of the time-to-front section: when it runs out the line is printed with what is there")
     ap.add_argument("--syn-instances", default="ap3_30_1,kp4_40_1",
                     help="instances for the cooperative (synergistic) workers, one per rank (N=1: min(k, contexts) on one GPU)")
     args = ap.parse_args()
@@ -385,24 +389,36 @@ def main():
                                 "detail": rt}
         if not args.no_fronts:
             line["cpu_baseline"]["front"], cpu_path = cpu_front_leg(tmp, cores)
-    # ---- time-to-front (every rank takes part in the sharded runs)
+    # ---- time-to-front (every rank takes part in the sharded runs).  A front job is one collective over all ranks and
+    # cannot be cancelled half way, so the section runs against a wall-clock budget: when it is spent, rank 0 prints the
+    # line with the entries finished so far (the unfinished one is named) and every rank leaves.
+    ttf = {}
+
+    def out_of_time():
+        if rank == 0:
+            ttf["unfinished"] = f"time-to-front budget of {args.front_budget_s:.0f} s spent"
+            print(json.dumps(line), flush=True)
+        os._exit(0)
+    watchdog = threading.Timer(args.front_budget_s, out_of_time)
+    watchdog.daemon = True
     if not args.no_fronts:
-        ttf = {}
+        watchdog.start()
+        if rank == 0:
+            line["time_to_front_s"] = ttf
         if world == 1:
             ttf["examples"] = example_fronts(mb, local)
             g = time_gpu_front(cpu_path, CPU_FRONT_INSTANCE, local)         # the CPU front leg's instance on the GPU, same mode
             line["cpu_baseline"]["front"]["gpu_seconds"] = g["seconds"]
             line["cpu_baseline"]["front"]["gpu_matches_golden"] = g["matches_golden"]
         ttf["examples --split -t 8"] = {stem: example_epp(stem, 8, local, tmp) for stem in ("4AP05", "4KP10")}
-        per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else 32
         for name in [x for x in args.front_instances.split(",") if x]:
+            per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else (16 if parse_instance(name)[1] <= 3 else 4)
             ttf[f"{name} --split -t {per_gpu * world}"] = synthetic_front(name, per_gpu * world, local, tmp)
         for name in [x for x in args.syn_instances.split(",") if x]:
             ttf[f"{name} synergistic"] = synergistic(name, local, tmp)
-        if rank == 0:
-            line["time_to_front_s"] = ttf
+    watchdog.cancel()
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -463,7 +479,8 @@ def _front_job(path, golden_rows, device, run):
     wall = time.perf_counter() - t
     st = be.stats()
     per_rank = _gather({"rank": d.rank, "busy_s": round(mine, 3), "ips": int(be.ip_count() - ips0),
-                        "node_lps": int(st.get("node_lps", 0)), "bb_nodes": int(st.get("bb_nodes", 0)), **(extra or {})})
+                        "node_lps": int(st.get("node_lps", 0)), "bb_nodes": int(st.get("bb_nodes", 0)),
+                        "strips_cut_by_idle_workers": be.pool.strips_stolen() if be._pool is not None else 0, **(extra or {})})
     walls = _gather(wall)
     return {"seconds": max(walls), "front": len(front),
             "matches_golden": ([list(r) for r in front] == golden_rows) if golden_rows is not None else None,
@@ -522,6 +539,7 @@ def example_epp(stem, threads, device, tmp):
         with open(p, "w") as fh:
             fh.write(e["input"])
     rows = [list(r) for r in parse_out(e["out"])[0]]
+    _front_job(p, rows, device, lambda be, d: (aira.epp_front(be, d, threads, False), None))        # untimed: first-touch of the pool's contexts
     out = _front_job(p, rows, device, lambda be, d: (aira.epp_front(be, d, threads, False), None))
     out.pop("per_rank")
     return out

@@ -226,6 +226,10 @@ int moip_pool_export_records(moip_pool* p, int cap, double* ip /* cap*k */, int*
                              int* infeasible /* cap */, int* n_out);
 int moip_pool_import_records(moip_pool* p, int n, const double* ip, const int* result, const int* infeasible);
 int moip_pool_exchange_counts(const moip_pool* p, int64_t* exported, int64_t* imported);
+/* Strips cut off busy strips by idle workers so far.  moip_pool_run_strips* starts with the strips it is given and lets a
+ * worker that finds none left take over the far half of the widest range a busy strip has not reached yet: a strip is
+ * only a range of the last objective (src/aira.cpp:1895-1916), so the front is the same (MOIP_NO_STEAL=1 disables). */
+int64_t moip_pool_strips_stolen(const moip_pool* p);
 int moip_pool_get_limit(moip_pool* p, int obj, int sense, const double* rhs, int* result, int* mip_status);
 /* split_optimise (src/aira.cpp:1886-1943) for nstrips explicit (start, stop) pairs, dealt dynamically to
  * the workers; rows_out receives the feasible result vectors (k ints per row, unsorted) */

@@ -110,6 +110,7 @@ _SIGS = {
     "moip_pool_export_records": (_i, [_vp, _i, _pd, _pi, _pi, _pi]),
     "moip_pool_import_records": (_i, [_vp, _i, _pd, _pi, _pi]),
     "moip_pool_exchange_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "moip_pool_strips_stolen": (C.c_int64, [_vp]),
     "moip_optimise": (_i, [_vp, C.POINTER(Worker), _vp, _vp]),
     "moip_optimise_with": (_i, [_i, _i, C.POINTER(Worker), SOLVE_FN, FIND_CB, INSERT_CB, _vp,
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -138,7 +139,10 @@ _SIGS = {
 }
 EXPORTED = sorted(_SIGS)
 for _name, (_res, _args) in _SIGS.items():
-    _fn = getattr(_lib, _name)          # AttributeError here = the library does not export the ABI
+    try:
+        _fn = getattr(_lib, _name)
+    except AttributeError as _e:        # the library does not export the ABI this module binds: stale build
+        raise ImportError(f"{LIB_PATH} does not export {_name}: rebuild it with `python moip_aira_b200/build.py --force`") from _e
     _fn.restype = _res
     _fn.argtypes = _args
 
@@ -453,6 +457,9 @@ class WorkerPool:
         inf = np.ascontiguousarray(infeasible, dtype=np.int32)
         if len(inf):
             _check(_lib.moip_pool_import_records(self._h, len(inf), _dp(ip), _ip(res), _ip(inf)), "pool_import_records")
+
+    def strips_stolen(self):
+        return int(_lib.moip_pool_strips_stolen(self._h))
 
     def exchange_counts(self):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -275,14 +275,30 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list 
             biggest, smallest = res[n_obj - 1], min([INT_MAX] + [s[n_obj - 1] for s in lower])
             if biggest == smallest:
                 smallest = INT_MIN
+        t_level = time.monotonic()
         strips = be.split_strips(biggest, smallest, num_threads, split_normal)
-        share = -(-len(strips) // dist.world) if dist.world > 1 else 0      # ceil: no rank claims more than its part at once
+        # Strip s belongs to rank s mod world: every rank gets an interleaved sample of the range -- light strips from its
+        # ends and heavy ones from its middle (the points crowd there) -- so the ranks carry about the same load without
+        # talking to each other; inside a rank, idle workers then cut busy strips in two (moip_pool_run_strips_claim).
+        # MOIP_GLOBAL_STRIP_COUNTER=1: the ranks draw strips from one job-wide counter in the c10d store instead.
+        if dist.world > 1 and not os.environ.get("MOIP_GLOBAL_STRIP_COUNTER"):
+            mine = iter([s_ for s_ in range(len(strips)) if s_ % dist.world == dist.rank] + [len(strips)] * 4096)
+            lock = __import__("threading").Lock()
+
+            def claim():
+                with lock:
+                    return next(mine, len(strips))
+            share = 0
+        else:
+            claim = dist.counter("level%d" % n_obj)
+            share = -(-len(strips) // dist.world) if dist.world > 1 else 0  # ceil: no rank claims more than its part at once
         endpoint = be.exchange_endpoint() if hasattr(be, "exchange_endpoint") else None
         with RecordExchange(dist, endpoint, k) as ex:
-            rows = be.run_strips(n_obj, strips, dist.counter("level%d" % n_obj), share)
+            rows = be.run_strips(n_obj, strips, claim, share)
         if stats is not None:
             stats.append({"n_obj": n_obj, "strips": len(strips), "exchange_rounds": ex.rounds, "records_sent": ex.sent,
-                          "records_received": ex.received, "rows_here": len(rows)})
+                          "records_received": ex.received, "rows_here": len(rows),
+                          "seconds": round(time.monotonic() - t_level, 3)})
         return dist.allgather_rows(rows, k)
 
     rows = level(k)

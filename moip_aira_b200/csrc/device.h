@@ -154,6 +154,16 @@ struct DevCache {
 int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queries, int sense, int* first_match,
               int* which, cudaStream_t st);
 
+// one query, answered into mapped pinned host memory (the generator's scan; see k3_scan1_kernel)
+struct K3Query { double ip[MOIP_MAX_OBJ]; };
+struct alignas(16) K3Answer {
+  CacheRecord rec;            // the matching record (valid when first_match >= 0)
+  int first_match, which;     // index in store `which` (0/1), or -1
+  int seq, pad;               // written last: the host polls it
+};
+int launch_k3_one(const DevCache& c0, const DevCache& c1, const K3Query& q, int sense, K3Answer* answer_dev, int seq,
+                  cudaStream_t st);
+
 // K4
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub,
                     int* xr /*[B][3][n]*/, long long* obj_out /*[B][3][k]*/, unsigned char* feasible_out /*[B][3]*/,

@@ -6,8 +6,12 @@
 //
 // State per worker: rhs[k] (current bounds), hi_seen[]/lo_seen[] (the reference's max[]/min[]
 // trackers), misses (its infcnt), last_missed (inflast), level (depth_level), walking (onwalk).
+#include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <mutex>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
@@ -32,6 +36,17 @@ struct GenBackend {
   virtual void outer_bound_moved(int /*objective*/, double /*new_rhs*/) {}
 };
 
+// A strip whose END can move while it is being solved: an idle worker of the pool takes over the far half of the range
+// a busy strip has not reached yet (moip_pool_run_strips_claim).  A strip is only a range of the last objective
+// (src/aira.cpp:1895-1916), its generator state is the bound vector and the trackers, so handing off [mid, stop) is just
+// "this strip now stops at mid" + a new strip that starts at mid; whatever the owner had already covered beyond mid when
+// it notices is solved twice, never lost.
+struct StripDyn {
+  std::atomic<double> stop{0.0};   // current end of the range (as in moip_worker::split_stop)
+  std::atomic<double> pos{0.0};    // bound of the last objective the owner is working under (its progress)
+  std::atomic<int> state{0};       // 0 free, 1 being solved, 2 done
+};
+
 namespace {
 
 // `max[d]-1` / `min[d]+1` in the reference are int expressions whose trackers may sit at
@@ -41,14 +56,14 @@ inline int wrap32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }
 
 }  // namespace
 
-int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* n_iter, int64_t* n_hit) {
+int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* n_iter, int64_t* n_hit, StripDyn* dyn = nullptr) {
   const bool is_min = sense == MOIP_SENSE_MIN;
   const double free_rhs = is_min ? kInf : -kInf;
   const int* perm = w.perm;
   const int n_obj = w.n_obj;
   const bool split = w.split != 0;
   const double split_start = w.split_start;
-  double split_stop = w.split_stop;
+  double stop_adj = 0.0;                             // the reference moves the end by one once the first point is known (:653-657)
   std::vector<double> rhs(k, free_rhs);
   std::vector<int> res(k, 0), hi_seen(k, 0), lo_seen(k, 0);
   int status = 0, rc;
@@ -58,7 +73,7 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
   const bool root_infeasible = status == MOIP_MIP_INFEASIBLE;
   if ((rc = be.insert(rhs.data(), res.data(), root_infeasible ? 1 : 0))) return rc;   // :644-651
   if (root_infeasible) return MOIP_OK;   // nothing lies inside these bounds (reference: trackers undefined)
-  if (split) split_stop += is_min ? -1.0 : 1.0;                             // :653-657
+  if (split) stop_adj = is_min ? -1.0 : 1.0;                                // :653-657
   hi_seen = res; lo_seen = res;                                             // :693-697
 
   auto tighten = [&](int d) {   // move the bound of objective d just past everything seen, reset its tracker
@@ -67,7 +82,13 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
   };
   // NB: the strip tests index rhs by position n_obj-1, not perm (src/aira.cpp:781, :882); EPP workers
   // use the identity permutation so both agree.
-  auto crossed_stop = [&]() { return is_min ? rhs[n_obj - 1] < split_stop : rhs[n_obj - 1] > split_stop; };
+  auto crossed_stop = [&]() {
+    const double split_stop = (dyn ? dyn->stop.load(std::memory_order_acquire) : w.split_stop) + stop_adj;
+    return is_min ? rhs[n_obj - 1] < split_stop : rhs[n_obj - 1] > split_stop;
+  };
+  auto publish_progress = [&](int active) {          // the strip's sweep proper: the last stage moves the bound of the last objective
+    if (dyn && split && active == n_obj - 1) dyn->pos.store(rhs[n_obj - 1], std::memory_order_release);
+  };
 
   for (int active = 1; active < n_obj; ++active) {                          // :723 objective_counter
     const int objective = perm[active];
@@ -79,10 +100,17 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
     rhs[objective] = is_min ? (double)wrap32((int64_t)hi_seen[objective] - 1)
                             : (double)wrap32((int64_t)lo_seen[objective] + 1);   // :761-777
     if (split && crossed_stop()) break;                                     // :778-801
+    publish_progress(active);
     if (!split && active == n_obj - 1) be.outer_bound_moved(objective, rhs[objective]);
     hi_seen[objective] = INT_MIN;                                           // :802-803
     lo_seen[objective] = INT_MAX;
+    long long spins = 0;
     while (misses < active) {                                               // :804
+      if (++spins % 200000 == 0 && std::getenv("MOIP_DEBUG_GEN"))
+        std::fprintf(stderr, "moip_b200: generator worker %d (n_obj %d, strip [%g, %g)) stage %d: %lld iterations, misses %d level %d walking %d rhs [%g %g %g %g] last result [%d %d %d %d] hi_seen [%d %d %d %d] lo_seen [%d %d %d %d]\n",
+                     w.id, n_obj, split_start, w.split_stop, active, spins, misses, level, (int)walking, rhs[0], k > 1 ? rhs[1] : 0.0, k > 2 ? rhs[2] : 0.0,
+                     k > 3 ? rhs[3] : 0.0, res[0], k > 1 ? res[1] : 0, k > 2 ? res[2] : 0, k > 3 ? res[3] : 0, hi_seen[0], k > 1 ? hi_seen[1] : 0,
+                     k > 2 ? hi_seen[2] : 0, k > 3 ? hi_seen[3] : 0, lo_seen[0], k > 1 ? lo_seen[1] : 0, k > 2 ? lo_seen[2] : 0, k > 3 ? lo_seen[3] : 0);
       int hit = 0, infeasible = 0;
       if ((rc = be.find(rhs.data(), &hit, &infeasible, res.data()))) return rc;   // :816-827
       if (n_iter) ++*n_iter;
@@ -106,6 +134,7 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
         for (int j = 0; j < k; ++j) rhs[j] = free_rhs;                      // :1586-1599
         if (split) rhs[n_obj - 1] = split_start;                            // :1649-1651
         tighten(objective);                                                 // :1655-1673
+        publish_progress(active);
         if (!split && active == n_obj - 1) be.outer_bound_moved(objective, rhs[objective]);
         level = 1; depth = perm[level]; walking = false;
       } else if (last_missed && misses != active) {
@@ -175,7 +204,13 @@ struct CallbackBackend : GenBackend {
 
 using namespace moip;
 
+static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles, moip::StripDyn* dyn);
+
 extern "C" int moip_optimise(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles) {
+  return optimise_strip(c, w, all, infeasibles, nullptr);
+}
+
+static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles, moip::StripDyn* dyn) {
   if (!c || !w || !all || !infeasibles || w->n_obj < 1 || w->n_obj > c->dm.k) return MOIP_ERR_ARG;
   const int sense = c->model->M.sense;
   moip_cache* local = nullptr;                       // `Solutions s(p.objcnt)` (src/aira.cpp:587)
@@ -183,7 +218,7 @@ extern "C" int moip_optimise(moip_ctx* c, const moip_worker* w, moip_cache* all,
   if (rc) return rc;
   GpuBackend be;
   be.c = c; be.infeasibles = infeasibles; be.sols = w->split ? all : local; be.sense = sense;
-  rc = run_worker(be, c->dm.k, sense, *w, nullptr, nullptr);
+  rc = run_worker(be, c->dm.k, sense, *w, nullptr, nullptr, dyn);
   if (!rc && moip_cache_size(local) > 0) {           // (EPP strips write straight into `all`: nothing to splice)
     moip_cache_sort_unique(local, nullptr, 0);       // :1877
     rc = moip_cache_merge(all, local);               // :1879
@@ -523,7 +558,7 @@ struct moip_pool {
   moip_cache* run_here = nullptr;
   moip_cache* run_inf = nullptr;
   size_t exp_cursor[2] = {0, 0};
-  int64_t exported = 0, imported = 0;
+  int64_t exported = 0, imported = 0, stolen = 0;
   cudaStream_t xstream = nullptr;            // imported records go to the device on this stream (created on first use)
 };
 
@@ -628,6 +663,8 @@ extern "C" int moip_pool_import_records(moip_pool* p, int n, const double* ip, c
   return MOIP_OK;
 }
 
+extern "C" int64_t moip_pool_strips_stolen(const moip_pool* p) { return p ? p->stolen : -1; }
+
 extern "C" int moip_pool_exchange_counts(const moip_pool* p, int64_t* exported, int64_t* imported) {
   if (!p) return MOIP_ERR_ARG;
   if (exported) *exported = p->exported;
@@ -683,9 +720,61 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   if (!p || p->ctx.empty() || nstrips < 0 || (nstrips > 0 && !start_stop) || !n_rows) return MOIP_ERR_ARG;
   const int k = p->ctx[0]->dm.k;
   if (n_obj < 1 || n_obj > k) return MOIP_ERR_ARG;
-  int W = std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
+  const int sense = p->ctx[0]->model->M.sense;
+  const bool is_min = sense == MOIP_SENSE_MIN;
+  // Work stealing (MOIP_STEAL=0 disables): a worker that finds no strip left takes over the far half of the widest range
+  // a busy strip has not reached yet.  Equal-width strips differ 10x in work (the points crowd in the middle of the last
+  // objective's range), and every additional strip pays for a lower-dimensional front of its own before it starts to
+  // sweep, so the level starts with few strips and splits only where, and when, a worker would otherwise idle.
+  const bool steal = nstrips > 0 && !std::getenv("MOIP_NO_STEAL");
+  int W = steal ? (int)p->ctx.size() : std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
   if (p->max_workers > 0) W = std::min(W, p->max_workers);
-  std::atomic<int> next(0), failed(0);
+  const int max_strips = nstrips + (steal ? 8 * W + 64 : 0);
+  std::vector<StripDyn> dyn((size_t)std::max(1, max_strips));
+  std::vector<double> sstart((size_t)std::max(1, max_strips), 0.0);
+  std::atomic<int> next(0), failed(0), n_dyn(nstrips), n_claiming(W), n_stolen(0);
+  std::mutex steal_mu;
+  // a cut must leave both halves worth a strip's start-up cost (a lower-dimensional front of its own): at least
+  // MOIP_STEAL_MIN units of the last objective (default 4) and 1/(8 W) of the level's range; at most 4 W cuts per level
+  double lo_edge = HUGE_VAL, hi_edge = -HUGE_VAL;
+  for (int t = 0; t < nstrips; ++t)
+    for (int e = 0; e < 2; ++e) {
+      const double v = start_stop[2 * t + e];
+      if (std::fabs(v) < 2147483647.0) { lo_edge = std::min(lo_edge, v); hi_edge = std::max(hi_edge, v); }
+    }
+  const double level_range = hi_edge > lo_edge ? hi_edge - lo_edge : 0.0;
+  const double min_steal = std::max(std::max(2.0, (double)(std::getenv("MOIP_STEAL_MIN") ? std::atoi(std::getenv("MOIP_STEAL_MIN")) : 4)),
+                                    level_range / (8.0 * std::max(1, W)));
+  const int max_steals = 4 * std::max(1, W);
+  // returns the index of a new strip cut off a busy one, -1 when nothing is worth cutting (yet), -2 when nothing is running
+  auto try_steal = [&]() -> int {
+    std::lock_guard<std::mutex> lk(steal_mu);
+    const int nd = n_dyn.load();
+    int victim = -1, running = 0;
+    double widest = 0.0;
+    for (int t = 0; t < nd; ++t) {
+      if (dyn[t].state.load(std::memory_order_acquire) != 1) continue;
+      ++running;
+      const double pos = dyn[t].pos.load(std::memory_order_acquire), stop = dyn[t].stop.load(std::memory_order_acquire);
+      if (std::fabs(pos) >= 2147483647.0 || std::fabs(stop) >= 2147483647.0) continue;   // open-ended ranges (INT_MIN / INT_MAX edges) are not cut
+      const double rem = is_min ? pos - stop : stop - pos;
+      if (rem > widest) { widest = rem; victim = t; }
+    }
+    if (running == 0) return -2;
+    if (victim < 0 || widest < 2.0 * min_steal || nd >= max_strips || n_stolen.load() >= max_steals) return -1;
+    const double pos = dyn[victim].pos.load(), stop = dyn[victim].stop.load();
+    // the strip that ends at the level's far edge -- the single-objective optimum of the last objective -- is not cut into
+    // narrow pieces: a cold start under a bound that close to the optimum is the one subproblem plain LP-based B&B is bad
+    // at (4KP n=40: 9e6 nodes for "f4 >= max - 8" alone, profiles/r02_fronts.md)
+    if (std::fabs(stop - (is_min ? lo_edge : hi_edge)) < 0.5 && widest / 2 < 0.05 * level_range) return -1;
+    const double mid = is_min ? pos - std::floor(widest / 2) : pos + std::floor(widest / 2);
+    sstart[nd] = mid;
+    dyn[nd].stop.store(stop); dyn[nd].pos.store(mid); dyn[nd].state.store(1, std::memory_order_release);
+    dyn[victim].stop.store(mid, std::memory_order_release);
+    n_dyn.store(nd + 1);
+    n_stolen.fetch_add(1);
+    return nd;
+  };
   // `here` and `infeasibles` are shared by the strips of a level, like the reference's threads share them
   // (src/aira.cpp:1918-1933); MOIP_POOL_PRIVATE_CACHES=1 gives every worker its own pair instead
   const bool shared = !std::getenv("MOIP_POOL_PRIVATE_CACHES");
@@ -706,29 +795,74 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
       rc = moip_cache_create(c, &here);
       if (!rc) rc = moip_cache_create(c, &infeasibles);
     }
+    bool claims_left = true;
     while (!rc && !failed.load()) {
-      const int t = claim ? claim(user) : next.fetch_add(1);
-      if (t < 0 || t >= nstrips) break;
+      int t = -1;
+      if (claims_left) {
+        t = claim ? claim(user) : next.fetch_add(1);
+        if (t < 0 || t >= nstrips) { claims_left = false; t = -1; n_claiming.fetch_sub(1); }
+        else {
+          sstart[t] = start_stop[2 * t];
+          dyn[t].stop.store(start_stop[2 * t + 1]); dyn[t].pos.store(start_stop[2 * t]);
+          dyn[t].state.store(1, std::memory_order_release);
+        }
+      }
+      if (t < 0) {
+        if (!steal || !shared || failed.load()) break;
+        t = try_steal();
+        if (t == -2 && n_claiming.load() == 0) break;                       // nothing running, nothing left to claim: the level is done
+        if (t < 0) { std::this_thread::sleep_for(std::chrono::microseconds(200)); continue; }
+      }
       moip_worker w{};
       w.id = t; w.n_obj = n_obj; w.split = 1;
       for (int i = 0; i < k; ++i) w.perm[i] = i;                            // thread.cpp:124-133
-      w.split_start = start_stop[2 * t]; w.split_stop = start_stop[2 * t + 1];
-      rc = moip_optimise(c, &w, here, infeasibles);
+      w.split_start = sstart[t]; w.split_stop = dyn[t].stop.load();
+      c->dbg_strip.store(t, std::memory_order_relaxed);
+      rc = optimise_strip(c, &w, here, infeasibles, steal && shared ? &dyn[t] : nullptr);
+      c->dbg_strip.store(-1, std::memory_order_relaxed);
+      dyn[t].state.store(2, std::memory_order_release);
     }
     if (!rc && here && !shared)
       for (auto& r : here->host) if (!r.infeasible) found[wi].insert(found[wi].end(), r.result, r.result + k);   // :1934-1942
     if (rc) failed.store(rc);
     if (!shared) { moip_cache_destroy(here); moip_cache_destroy(infeasibles); }
   };
+  // MOIP_WATCHDOG=<seconds>: a thread that reports what every worker is doing (strip, B&B round of the current IP, open
+  // nodes, IPs solved so far) -- the counterpart of the reference's DEBUG prints for a run that seems stuck
+  std::atomic<bool> watch_stop(false);
+  std::thread watchdog;
+  if (const char* ws = std::getenv("MOIP_WATCHDOG")) {
+    const double every = std::max(0.5, std::atof(ws));
+    watchdog = std::thread([&, every] {
+      double waited = 0;
+      while (!watch_stop.load()) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        waited += 0.1;
+        if (waited < every) continue;
+        waited = 0;
+        for (int wi = 0; wi < W; ++wi) {
+          moip_ctx* c = p->ctx[wi];
+          const long long t = c->dbg_strip.load();
+          std::fprintf(stderr, "moip_b200: watchdog: worker %d strip %lld [%g -> %g, at %g] %s round %lld open %lld; %lld IPs %lld nodes so far\n", wi, t,
+                       t >= 0 ? sstart[t] : 0.0, t >= 0 ? dyn[t].stop.load() : 0.0, t >= 0 ? dyn[t].pos.load() : 0.0,
+                       c->dbg_where.load() == 1 ? "cache scan" : (c->dbg_where.load() == 2 ? "B&B" : "generator"), c->dbg_rounds.load(),
+                       c->dbg_open.load(), (long long)c->stats.ip_solved, (long long)c->stats.bb_nodes);
+        }
+      }
+    });
+  }
   std::vector<std::thread> th;
   for (int wi = 1; wi < W; ++wi) th.emplace_back(work, wi);
   work(0);
   for (auto& t : th) t.join();
+  watch_stop.store(true);
+  if (watchdog.joinable()) watchdog.join();
   if (shared) {
     {
       std::lock_guard<std::mutex> rl(p->run_mu);
       p->run_here = nullptr; p->run_inf = nullptr;
     }
+    p->stolen += n_stolen.load();
     if (!failed.load())      // (records imported from other ranks are reported by the rank that found them)
       for (auto& r : sh_here->host) if (!r.infeasible && !r.pad[0]) found[0].insert(found[0].end(), r.result, r.result + k);
     moip_cache_destroy(sh_here);

@@ -467,7 +467,8 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
         if (role & ROLE_LEADER) ytsh[row] = r_yt;
         if (check_it) next_check += p.check_every;
         __syncthreads();                   // ytsh visible
-        double aC[4] = {0, 0, 0, 0};       // pobj, dual (columns), dual (rows), primal residual^2 (unscaled)
+        // pobj, dual (columns), dual (rows), primal residual^2 (unscaled), Farkas value (columns), sum of its |terms|
+        double aC[6] = {0, 0, 0, 0, 0, 0};
         double ytd[KD];
 #pragma unroll
         for (int d = 0; d < KD; ++d) ytd[d] = ytsh[msS + d];
@@ -483,15 +484,22 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
           const double r = cj - g;
           aC[0] = fma(cj, xts_t[c * NT], aC[0]);
           aC[1] += (r > 0) ? r * bx.x : r * bx.y;
+          const double fk = (g < 0) ? -g * bx.x : -g * bx.y;        // the same bound with the objective dropped (Farkas)
+          aC[4] += fk; aC[5] += fabs(fk);
         }
         if (role & ROLE_LIVE) {
           if (r_yt > 0) aC[2] = -r_yt * r_nlo;
           else if (r_yt < 0) aC[2] = -r_yt * r_nhi;
+          aC[5] += fabs(aC[2]);
           const double viol = dmax(0.0, dmax(r_sxt + r_nhi, -r_nlo - r_sxt)) / dm.dr_k[row];
           aC[3] = viol * viol;
         }
-        bsum<4, NT>(aC, redC, tid);
+        bsum<6, NT>(aC, redC, tid);
         const double pobj = aC[0], dobj = aC[1] + aC[2];
+        // Farkas certificate: F(y) = min over the box of (-S^T y) x + (y+ lo - y- hi) <= 0 for every point that satisfies
+        // the rows, so F(y) > 0 proves the node LP infeasible -- long before the Lagrangian bound (the same sum plus the
+        // objective) climbs past the objective's maximum on the box.  The margin is 1000x the rounding error of the sum.
+        const bool farkas = aC[4] + aC[2] > 1e-9 * aC[5] + 1e-9;
         double best_lb = cold[COLD_BEST_LB];
         const double obj_upper = cold[COLD_OBJ_UPPER], kkt_binv = cold[COLD_KKT_BINV];
         if (p.fixed_iters > 0) best_lb = dobj;
@@ -501,7 +509,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
           const double rel = dmax(sqrt(aC[3]) * kkt_binv, gap / (1.0 + fabs(pobj) + fabs(dobj)));
           const double cutoff = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
           if (best_lb >= cutoff - p.cutoff_slack) { status = MOIP_LP_CUTOFF; stop = true; }
-          else if (best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
+          else if (farkas || best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
           else if (rel <= p.eps) { status = MOIP_LP_CONVERGED; stop = true; }
           else if (p.int_obj && sqrt(aC[3]) * kkt_binv <= 1e-5 && ceil(best_lb - 1e-6) >= ceil(pobj - 1e-3)) {
             status = MOIP_LP_CONVERGED; stop = true;      // the integer-rounded bound cannot improve any further

@@ -298,15 +298,20 @@ k1_small_kernel(const DevModel dm, const LpBatch b, const LpParams p) {
         const double r = cj - g;
         c8[0] = fma(cj, xts_t[c * NT], c8[0]);
         c8[1] += (r > 0) ? r * bx.x : r * bx.y;
+        const double fk = (g < 0) ? -g * bx.x : -g * bx.y;          // the same bound with the objective dropped (Farkas)
+        c8[4] += fk; c8[5] += fabs(fk);
       }
       if (live) {
         if (r_yt > 0) c8[2] = -r_yt * r_nlo;
         else if (r_yt < 0) c8[2] = -r_yt * r_nhi;
+        c8[5] += fabs(c8[2]);
         const double viol = dmax(0.0, dmax(r_sxt + r_nhi, -r_nlo - r_sxt)) / dr_mine;
         c8[3] = viol * viol;
       }
       const double s = reduce8(c8, gl);
       const double pobj = shi(s, gbase), dobj = shi(s, gbase + 1) + shi(s, gbase + 2), pres2 = shi(s, gbase + 3);
+      // Farkas certificate (see k1_reg.cuh): F(y) > 0 proves the node LP infeasible
+      const bool farkas = shi(s, gbase + 4) + shi(s, gbase + 2) > 1e-9 * shi(s, gbase + 5) + 1e-9;
       if (eval_it) {
         if (check_it) next_check += p.check_every;
         double best_lb = cold_g[COLD_BEST_LB];
@@ -318,7 +323,7 @@ k1_small_kernel(const DevModel dm, const LpBatch b, const LpParams p) {
           const double rel = dmax(sqrt(pres2) * kkt_binv, gap / (1.0 + fabs(pobj) + fabs(dobj)));
           const double cutoff = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
           if (best_lb >= cutoff - p.cutoff_slack) { status = MOIP_LP_CUTOFF; stop = true; }
-          else if (best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
+          else if (farkas || best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
           else if (rel <= p.eps) { status = MOIP_LP_CONVERGED; stop = true; }
           else if (p.int_obj && sqrt(pres2) * kkt_binv <= 1e-5 && ceil(best_lb - 1e-6) >= ceil(pobj - 1e-3)) {
             status = MOIP_LP_CONVERGED; stop = true;      // the integer-rounded bound cannot improve any further

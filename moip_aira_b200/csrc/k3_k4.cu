@@ -64,6 +64,66 @@ __global__ void __launch_bounds__(NT) k3_scan_kernel(const DevCache c0, const De
   }
 }
 
+// The generator's scan: ONE query against the two stores (infeasibles, then solutions: src/aira.cpp:816-823).  The query
+// arrives as a kernel parameter and the answer -- index, store and the matching record itself -- is written straight into
+// mapped pinned host memory, published by a sequence number the host polls: no H2D / D2H copy, no stream synchronise.
+template <int NT>
+__global__ void __launch_bounds__(NT) k3_scan1_kernel(const DevCache c0, const DevCache c1, const K3Query q, const int sense,
+                                                      K3Answer* answer, const int seq) {
+  __shared__ int s_best;
+  const int tid = threadIdx.x;
+  const int k = c0.k;
+  int found = -1, found_in = -1;
+  for (int st = 0; st < 2 && found < 0; ++st) {
+    const DevCache& c = st == 0 ? c0 : c1;
+    if (c.size <= 0) continue;
+    if (tid == 0) s_best = INT_MAX;
+    __syncthreads();
+    for (int base = 0; base < c.size; base += NT) {
+      const int r = base + tid;
+      bool ok = r < c.size;
+      if (ok) {
+        const int4* p = reinterpret_cast<const int4*>(c.rec + r);
+        const int4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
+        double rip[4];
+        rip[0] = __hiloint2double(v0.y, v0.x); rip[1] = __hiloint2double(v0.w, v0.z);
+        rip[2] = __hiloint2double(v1.y, v1.x); rip[3] = __hiloint2double(v1.w, v1.z);
+        const int res[4] = {v2.x, v2.y, v2.z, v2.w};
+        const bool inf = v3.x != 0;
+#pragma unroll
+        for (int i = 0; i < MOIP_MAX_OBJ; ++i) {
+          if (i < k) {
+            if (sense == MOIP_SENSE_MIN) {
+              if (rip[i] < q.ip[i]) ok = false;                         // t1 (src/solutions.cpp:20)
+              if (!inf && (double)res[i] > q.ip[i]) ok = false;         // t3 (:25-30)
+            } else {
+              if (rip[i] > q.ip[i]) ok = false;                         // t1 (:35)
+              if (!inf && (double)res[i] < q.ip[i]) ok = false;         // t3 (:40-45)
+            }
+          }
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (bal && (tid & 31) == 0) atomicMin(&s_best, base + (tid & ~31) + (__ffs(bal) - 1));
+      __syncthreads();
+      const bool hit = s_best != INT_MAX;   // uniform: read between the two barriers
+      __syncthreads();
+      if (hit) break;
+    }
+    if (s_best != INT_MAX) { found = s_best; found_in = st; }
+    __syncthreads();
+  }
+  if (tid < 16 && found >= 0)              // the record itself: the host need not touch the store again
+    reinterpret_cast<int*>(&answer->rec)[tid] = reinterpret_cast<const int*>((found_in == 0 ? c0 : c1).rec + found)[tid];
+  __syncthreads();
+  if (tid == 0) {
+    answer->first_match = found;
+    answer->which = found_in;
+    __threadfence_system();                // answer before its sequence number, all the way to host memory
+    *reinterpret_cast<volatile int*>(&answer->seq) = seq;
+  }
+}
+
 __device__ __forceinline__ long long warp_sum_ll(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -186,6 +246,15 @@ int launch_k3(const DevCache& c0, const DevCache& c1, int Q, const double* queri
   if (set_aux_carveout(k3_scan_kernel<128>, carve)) return MOIP_ERR_CUDA;
   int grid = Q < 148 * 16 ? Q : 148 * 16;
   k3_scan_kernel<128><<<grid, 128, 0, st>>>(c0, c1, Q, queries, sense, first_match, which);
+  MOIP_CUDA(cudaGetLastError());
+  return MOIP_OK;
+}
+
+int launch_k3_one(const DevCache& c0, const DevCache& c1, const K3Query& q, int sense, K3Answer* answer_dev, int seq,
+                  cudaStream_t st) {
+  static LaunchCfg carve;
+  if (set_aux_carveout(k3_scan1_kernel<512>, carve)) return MOIP_ERR_CUDA;
+  k3_scan1_kernel<512><<<1, 512, 0, st>>>(c0, c1, q, sense, answer_dev, seq);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }

@@ -5,6 +5,7 @@
 #include "solver.h"
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -148,6 +149,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->bb_levels = env_int("MOIP_BB_LEVELS", 3);
   c->use_points = env_int("MOIP_POINT_STORE", 1) != 0;
   c->use_fused = env_int("MOIP_FUSED_ROUND", 1) != 0;
+  c->k3_poll = env_int("MOIP_K3_POLL", 1) != 0;
   {
     std::unique_lock<std::shared_mutex> lk(m->points.mu);
     if (m->points.n == 0) {
@@ -192,6 +194,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->kev) if (e) cudaEventDestroy(e);
+  if (c->k3_answer) cudaFreeHost(c->k3_answer);
   for (void* p : c->model_allocs) cudaFree(p);
   c->b_cost.release(); c->b_lb.release(); c->b_ub.release(); c->b_status.release(); c->b_iters.release();
   c->b_branch.release(); c->b_counter.release(); c->b_rhs.release(); c->b_pobj.release(); c->b_dbound.release();
@@ -404,6 +407,8 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
                 CacheRecord* rec_out) {
   MOIP_CUDA(cudaSetDevice(c->device));
   const int k = c->dm.k;
+  c->dbg_where.store(1, std::memory_order_relaxed);
+  struct Leave { moip_ctx* c; ~Leave() { c->dbg_where.store(0, std::memory_order_relaxed); } } leave{c};
   DevCache e{}; e.k = k; e.size = 0; e.rec = nullptr;
   DevCache v0 = e, v1 = e;
   if (s0) {
@@ -415,6 +420,40 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
     std::lock_guard<std::mutex> lk(s1->mu);
     if (s1->sync_to_device(c->stream)) return MOIP_ERR_CUDA;
     v1 = s1->view();
+  }
+  if (Q == 1 && rec_out && c->k3_poll) {
+    // the generator's scan: query by kernel parameter, answer into mapped pinned memory, host polls the sequence number
+    if (!c->k3_answer) {
+      MOIP_CUDA(cudaHostAlloc((void**)&c->k3_answer, sizeof(K3Answer), cudaHostAllocMapped));
+      MOIP_CUDA(cudaHostGetDevicePointer((void**)&c->k3_answer_dev, c->k3_answer, 0));
+      std::memset(c->k3_answer, 0, sizeof(K3Answer));
+    }
+    K3Query qq{};
+    for (int i = 0; i < k; ++i) qq.ip[i] = ip[i];
+    const int seq = ++c->k3_seq;
+    c->kmark(8);
+    int rc = launch_k3_one(v0, v1, qq, sense, c->k3_answer_dev, seq, c->stream);
+    if (rc) return rc;
+    c->kmark(9);
+    c->stats.kernel_launches += 1;
+    c->stats.cache_queries += 1;
+    volatile int* vseq = &c->k3_answer->seq;
+    for (long spins = 0; *vseq != seq; ++spins) {
+      if ((spins & 0xfff) == 0xfff) {                    // a failed launch would never publish: ask the stream now and then
+        const cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) { MOIP_CUDA(e); }
+        if (e == cudaSuccess && *vseq != seq) { MOIP_CUDA(cudaStreamSynchronize(c->stream)); break; }
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (c->ktiming) { cudaEventSynchronize(c->kev[9]); c->ktimes.k3_ms += c->kspan(8, 9); c->ktimes.scans += 1; }
+    first_match[0] = c->k3_answer->first_match;
+    if (which) which[0] = c->k3_answer->which;
+    if (first_match[0] >= 0) rec_out[0] = c->k3_answer->rec;
+    return MOIP_OK;
   }
   if (c->q_ip.ensure((size_t)Q * k) || c->q_out.ensure(Q) || c->q_which.ensure(Q) || c->h_q.ensure((size_t)2 * Q)) return MOIP_ERR_CUDA;
   c->kmark(8);
@@ -550,6 +589,9 @@ int moip_ctx::alloc_slot() {
   return s;
 }
 
+// (The thread-sanitizer build of the HOST code, tests/tsan, compiles this file with MOIP_HOST_DOUBLE and supplies an
+// enumeration solve_ip of its own: everything else in this file -- contexts, caches, lexicographic chain -- is the code under test.)
+#ifndef MOIP_HOST_DOUBLE
 namespace {
 struct OpenNode {
   int slot;
@@ -693,6 +735,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     if (B == 0) break;
     stats.bb_nodes += B;
     stage_nodes[cur_stage] += B; stage_rounds[cur_stage] += 1; ++ip_rounds;
+    dbg_where.store(2, std::memory_order_relaxed); dbg_rounds.store(ip_rounds, std::memory_order_relaxed); dbg_open.store((long long)open.size() + B, std::memory_order_relaxed);
     // ---- device round: propagate -> gather -> LP -> scatter/round -> verify
     std::vector<long long> plo = olo, phi = ohi;
     if (have_inc) {   // incumbent cut-off row on the optimised objective: must be strictly better
@@ -890,6 +933,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     if (prof) { const double tp3 = now_s(); prof_t[0] += tp1 - tp0; prof_t[1] += tp2 - tp1; prof_t[2] += tp3 - tp2; prof_t[3] += 1; prof_t[4] += B; }
   }
   for (auto& nd : open) free_slots.push_back(nd.slot);
+  dbg_where.store(0, std::memory_order_relaxed);
   if (ip_rounds <= 1) stage_root_solved[cur_stage] += 1;
   if (have_inc) {
     if (inc_on_device) {
@@ -913,6 +957,8 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   }
   return MOIP_OK;
 }
+
+#endif  // MOIP_HOST_DOUBLE
 
 // int solve(Env&, Problem&, int* result, double* rhs, Thread* t)  -- reference src/aira.cpp:452-536
 int moip_ctx::lex_solve(const int* perm, int n_obj, const double* rhs, int* result, int* mip_status) {

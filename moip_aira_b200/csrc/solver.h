@@ -2,6 +2,7 @@
 #pragma once
 #include <chrono>
 #include <array>
+#include <atomic>
 #include <mutex>
 #include <set>
 #include <shared_mutex>
@@ -151,6 +152,10 @@ struct moip_ctx {
   moip::DBuf<double> q_ip;
   moip::DBuf<int> q_out, q_which;
   moip::HBuf<int> h_q;
+  moip::K3Answer* k3_answer = nullptr;       // mapped pinned: the single-query scan writes its answer here
+  moip::K3Answer* k3_answer_dev = nullptr;   // the same memory as the device sees it
+  int k3_seq = 0;
+  bool k3_poll = true;                       // MOIP_K3_POLL=0: always the copy + synchronise path
   moip::DBuf<int> v_x;
   moip::DBuf<double> v_rhs;
   moip::DBuf<long long> v_obj;
@@ -195,6 +200,9 @@ struct moip_ctx {
             stage_lps[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0}, stage_rounds[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0},
             stage_root_solved[MOIP_MAX_OBJ + 1] = {0, 0, 0, 0, 0};   // per stage of the lexicographic chain (MOIP_PROFILE_ROUNDS)
   int cur_stage = MOIP_MAX_OBJ;       // stage of the IP being solved (MOIP_MAX_OBJ = outside lex_solve)
+  // what the worker is doing right now, for the pool's watchdog (MOIP_WATCHDOG=<seconds>): 0 idle, 1 cache scan, 2 B&B round
+  std::atomic<int> dbg_where{0};
+  std::atomic<long long> dbg_rounds{0}, dbg_open{0}, dbg_strip{-1};
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
   moip::DBuf<double> k1_scratch;   // streaming mode of the generic K1 kernel (models too large for shared memory)

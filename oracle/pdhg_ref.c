@@ -160,7 +160,7 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
     }
     int stop = 0;
     if ((fixed_iters <= 0 && (it % check_every) == 0) || (fixed_iters > 0 && it >= iter_cap)) {
-      double po = 0, dcol = 0, drow = 0, pres2 = 0;
+      double po = 0, dcol = 0, drow = 0, pres2 = 0, fcol = 0, fabs_sum = 0;
       for (int j = 0; j < n; ++j) g[j] = 0;
       for (int i = 0; i < m; ++i) {
         const double yi = yt[i];
@@ -170,9 +170,13 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
         double r = c[j] - g[j];
         po += c[j] * 0.5 * (xbar[j] + x[j]);
         dcol += (r > 0) ? r * l[j] : r * u[j];
+        double fk = (g[j] < 0) ? -g[j] * l[j] : -g[j] * u[j];       /* the same bound with the objective dropped (Farkas) */
+        fcol += fk; fabs_sum += fabs(fk);
       }
       for (int i = 0; i < m; ++i) {
-        if (yt[i] > 0) drow += yt[i] * lo[i]; else if (yt[i] < 0) drow += yt[i] * hi[i];
+        double rt = 0;
+        if (yt[i] > 0) rt = yt[i] * lo[i]; else if (yt[i] < 0) rt = yt[i] * hi[i];
+        drow += rt; fabs_sum += fabs(rt);
         double viol = fmax(0.0, fmax(sxt[i] - hi[i], lo[i] - sxt[i])) / s->dr[i];
         if (!(isinf(lo[i]) && isinf(hi[i]))) pres2 += viol * viol;
       }
@@ -184,7 +188,8 @@ static void solve_node(const scaled_t* s, const double* c_un, const double* lo_u
         double gap = fabs(pobj - dobj);
         double rel = fmax(sqrt(pres2) / kkt_bden, gap / (1.0 + fabs(pobj) + fabs(dobj)));
         if (best_lb >= cutoff - cutoff_slack) { status = ST_CUTOFF; stop = 1; }
-        else if (best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = ST_INFEASIBLE; stop = 1; }
+        /* Farkas certificate: fcol + drow > 0 proves infeasibility (the K1 kernels test the same quantity) */
+        else if (fcol + drow > 1e-9 * fabs_sum + 1e-9 || best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = ST_INFEASIBLE; stop = 1; }
         else if (rel <= eps) { status = ST_CONVERGED; stop = 1; }
       }
     }

@@ -392,6 +392,17 @@ def test_front_synthetic_golden_pool(mb, tmp_path, name, strips, workers):
     pool.close()
 
 
+@pytest.mark.parametrize("name,strips,workers", [("ap3_12_1", 2, 8), ("kp4_25_1", 1, 6), ("ap3_15_1", 3, 12)])
+def test_pool_work_stealing(mb, tmp_path, name, strips, workers):
+    """Fewer strips than workers: the idle workers cut the busy strips' remaining ranges in two (moip_pool_run_strips_claim).
+    A strip is only a range of the last objective (src/aira.cpp:1895-1916), so the front must not change."""
+    path, want = _synthetic_case(name, tmp_path)
+    pool = mb.WorkerPool(mb.Problem(path), 0, workers)
+    assert pool.pareto_front(strips) == want
+    assert pool.strips_stolen() > 0
+    pool.close()
+
+
 def test_front_synthetic_vs_bruteforce(mb, tmp_path):
     """Synthetic assignment / knapsack instances against the solver-free brute-force front."""
     from oracle import aira_oracle as ao
