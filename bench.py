@@ -412,7 +412,8 @@ def main():
             line["cpu_baseline"]["front"]["gpu_matches_golden"] = g["matches_golden"]
         ttf["examples --split -t 8"] = {stem: example_epp(stem, 8, local, tmp) for stem in ("4AP05", "4KP10")}
         for name in [x for x in args.front_instances.split(",") if x]:
-            per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else (16 if parse_instance(name)[1] <= 3 else 4)
+            from moip_aira_b200 import aira
+            per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else (aira.default_workers() if parse_instance(name)[1] <= 3 else 4)
             ttf[f"{name} --split -t {per_gpu * world}"] = synthetic_front(name, per_gpu * world, local, tmp)
         for name in [x for x in args.syn_instances.split(",") if x]:
             ttf[f"{name} synergistic"] = synergistic(name, local, tmp)
@@ -480,7 +481,10 @@ def _front_job(path, golden_rows, device, run):
     st = be.stats()
     per_rank = _gather({"rank": d.rank, "busy_s": round(mine, 3), "ips": int(be.ip_count() - ips0),
                         "node_lps": int(st.get("node_lps", 0)), "bb_nodes": int(st.get("bb_nodes", 0)),
-                        "strips_cut_by_idle_workers": be.pool.strips_stolen() if be._pool is not None else 0, **(extra or {})})
+                        "strips_cut_by_idle_workers": be.pool.strips_stolen() if be._pool is not None else 0,
+                        "solver_s": round(float(st.get("solver_seconds", 0.0)), 2),
+                        "kernel_ms": ({a: round(v) for a, v in be.pool.kernel_times().items()} if os.environ.get("MOIP_KERNEL_TIMING") and be._pool is not None else None),
+                        **(extra or {})})
     walls = _gather(wall)
     return {"seconds": max(walls), "front": len(front),
             "matches_golden": ([list(r) for r in front] == golden_rows) if golden_rows is not None else None,

@@ -172,6 +172,9 @@ typedef struct {
   int64_t scans;           /* K3 launches timed */
 } moip_kernel_times;
 int moip_ctx_set_kernel_timing(moip_ctx* c, int on);
+/* how the context's owner waits for a B&B round: 0 = spin in the driver (lowest latency, one core per worker), 1 = sleep on
+ * a blocking event (for more workers than cores).  MOIP_SYNC=spin|block overrides; pools choose by core count (auto). */
+int moip_ctx_set_sync_mode(moip_ctx* c, int blocking);
 int moip_ctx_kernel_times(const moip_ctx* c, moip_kernel_times* out);
 
 /* ---- subproblem generator re-hosted on the boundary above (src/aira.cpp:538-1884 without the

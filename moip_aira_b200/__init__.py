@@ -103,6 +103,7 @@ _SIGS = {
     "moip_ctx_stats": (_i, [_vp, C.POINTER(Stats)]),
     "moip_ctx_reset_stats": (_i, [_vp]),
     "moip_ctx_set_kernel_timing": (_i, [_vp, _i]),
+    "moip_ctx_set_sync_mode": (_i, [_vp, _i]),
     "moip_ctx_kernel_times": (_i, [_vp, C.POINTER(KernelTimes)]),
     "moip_pool_set_kernel_timing": (_i, [_vp, _i]),
     "moip_pool_kernel_times": (_i, [_vp, C.POINTER(KernelTimes)]),

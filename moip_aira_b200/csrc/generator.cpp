@@ -16,6 +16,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdint>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -562,10 +563,24 @@ struct moip_pool {
   cudaStream_t xstream = nullptr;            // imported records go to the device on this stream (created on first use)
 };
 
+extern "C" int moip_ctx_set_sync_mode(moip_ctx* c, int blocking);
+
 extern "C" int moip_pool_create(moip_model* m, int device, int workers, moip_pool** out) {
   if (!m || !out || workers < 1 || workers > 64) return MOIP_ERR_ARG;
   moip_pool* p = new moip_pool();
   p->model = m; p->device = device;
+  // MOIP_SYNC=auto (default): the workers sleep on a blocking event instead of spinning when, together with the pools of
+  // the other ranks on this host (LOCAL_WORLD_SIZE, set by torchrun), they outnumber the cores
+  bool block = false;
+  {
+    const char* sm = std::getenv("MOIP_SYNC");
+    if (!sm || std::strcmp(sm, "auto") == 0) {
+      const char* lw = std::getenv("LOCAL_WORLD_SIZE");
+      const long ranks = lw ? std::max(1, std::atoi(lw)) : 1;
+      const long cores = std::max(1u, std::thread::hardware_concurrency());
+      block = (long)workers * ranks + 2 * ranks > cores;
+    } else block = std::strcmp(sm, "block") == 0;
+  }
   for (int w = 0; w < workers; ++w) {
     cudaStream_t st = nullptr;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) {
@@ -577,6 +592,7 @@ extern "C" int moip_pool_create(moip_model* m, int device, int workers, moip_poo
     moip_ctx* c = nullptr;
     int rc = moip_ctx_create(m, device, st, &c);
     if (rc) { moip_pool_destroy(p); return rc; }
+    moip_ctx_set_sync_mode(c, block ? 1 : 0);
     p->ctx.push_back(c);
   }
   *out = p;
@@ -729,13 +745,16 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   const bool steal = nstrips > 0 && !std::getenv("MOIP_NO_STEAL");
   int W = steal ? (int)p->ctx.size() : std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
   if (p->max_workers > 0) W = std::min(W, p->max_workers);
-  const int max_strips = nstrips + (steal ? 8 * W + 64 : 0);
+  const int max_strips = nstrips + (steal ? 8 * W + 64 : 0);   // (>= nstrips + max_steals below)
   std::vector<StripDyn> dyn((size_t)std::max(1, max_strips));
   std::vector<double> sstart((size_t)std::max(1, max_strips), 0.0);
+  std::vector<int> cut_from((size_t)std::max(1, max_strips), -1);
   std::atomic<int> next(0), failed(0), n_dyn(nstrips), n_claiming(W), n_stolen(0);
   std::mutex steal_mu;
   // a cut must leave both halves worth a strip's start-up cost (a lower-dimensional front of its own): at least
-  // MOIP_STEAL_MIN units of the last objective (default 4) and 1/(8 W) of the level's range; at most 4 W cuts per level
+  // MOIP_STEAL_MIN units of the last objective (default 2) and 1/(MOIP_STEAL_FRAC W) of the level's range (default 16 W);
+  // at most 8 W cuts per level.  An idle worker costs nothing, so the thresholds are low: the start-up of a cut-off
+  // strip is paid by a worker that had nothing else to do.
   double lo_edge = HUGE_VAL, hi_edge = -HUGE_VAL;
   for (int t = 0; t < nstrips; ++t)
     for (int e = 0; e < 2; ++e) {
@@ -743,9 +762,10 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
       if (std::fabs(v) < 2147483647.0) { lo_edge = std::min(lo_edge, v); hi_edge = std::max(hi_edge, v); }
     }
   const double level_range = hi_edge > lo_edge ? hi_edge - lo_edge : 0.0;
-  const double min_steal = std::max(std::max(2.0, (double)(std::getenv("MOIP_STEAL_MIN") ? std::atoi(std::getenv("MOIP_STEAL_MIN")) : 4)),
-                                    level_range / (8.0 * std::max(1, W)));
-  const int max_steals = 4 * std::max(1, W);
+  const double steal_frac = std::getenv("MOIP_STEAL_FRAC") ? std::atof(std::getenv("MOIP_STEAL_FRAC")) : 16.0;
+  const double min_steal = std::max(std::max(1.0, (double)(std::getenv("MOIP_STEAL_MIN") ? std::atoi(std::getenv("MOIP_STEAL_MIN")) : 2)),
+                                    level_range / (std::max(1.0, steal_frac) * std::max(1, W)));
+  const int max_steals = 8 * std::max(1, W);
   // returns the index of a new strip cut off a busy one, -1 when nothing is worth cutting (yet), -2 when nothing is running
   auto try_steal = [&]() -> int {
     std::lock_guard<std::mutex> lk(steal_mu);
@@ -769,6 +789,7 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
     if (std::fabs(stop - (is_min ? lo_edge : hi_edge)) < 0.5 && widest / 2 < 0.05 * level_range) return -1;
     const double mid = is_min ? pos - std::floor(widest / 2) : pos + std::floor(widest / 2);
     sstart[nd] = mid;
+    cut_from[nd] = victim;
     dyn[nd].stop.store(stop); dyn[nd].pos.store(mid); dyn[nd].state.store(1, std::memory_order_release);
     dyn[victim].stop.store(mid, std::memory_order_release);
     n_dyn.store(nd + 1);
@@ -787,6 +808,12 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
     p->run_here = sh_here; p->run_inf = sh_inf; p->exp_cursor[0] = p->exp_cursor[1] = 0;
   }
   std::vector<std::vector<int>> found(W);
+  // MOIP_STRIP_TIMELINE=1: one line per strip at the end of the level (who solved it, when, how many IPs, cut off whom)
+  struct StripLog { int worker = -1, from = -1; double t0 = 0, t1 = 0, start = 0, stop0 = 0, stop1 = 0; long long ips = 0; };
+  const bool timeline = std::getenv("MOIP_STRIP_TIMELINE") != nullptr;
+  std::vector<StripLog> slog(timeline ? (size_t)std::max(1, max_strips) : 0);
+  const auto t_level0 = std::chrono::steady_clock::now();
+  auto since0 = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_level0).count(); };
   auto work = [&](int wi) {
     moip_ctx* c = p->ctx[wi];
     moip_cache *here = sh_here, *infeasibles = sh_inf;
@@ -818,7 +845,9 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
       for (int i = 0; i < k; ++i) w.perm[i] = i;                            // thread.cpp:124-133
       w.split_start = sstart[t]; w.split_stop = dyn[t].stop.load();
       c->dbg_strip.store(t, std::memory_order_relaxed);
+      if (timeline) { slog[t].worker = wi; slog[t].t0 = since0(); slog[t].start = sstart[t]; slog[t].stop0 = w.split_stop; slog[t].ips = c->stats.ip_solved; slog[t].from = cut_from[t]; }
       rc = optimise_strip(c, &w, here, infeasibles, steal && shared ? &dyn[t] : nullptr);
+      if (timeline) { slog[t].t1 = since0(); slog[t].stop1 = dyn[t].stop.load(); slog[t].ips = c->stats.ip_solved - slog[t].ips; }
       c->dbg_strip.store(-1, std::memory_order_relaxed);
       dyn[t].state.store(2, std::memory_order_release);
     }
@@ -857,6 +886,15 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   for (auto& t : th) t.join();
   watch_stop.store(true);
   if (watchdog.joinable()) watchdog.join();
+  if (timeline) {
+    const char* rk = std::getenv("RANK");
+    for (int t = 0; t < n_dyn.load(); ++t)
+      if (slog[t].worker >= 0)
+        std::fprintf(stderr, "moip_b200: timeline rank %s level %d strip %d%s worker %d: %.3f -> %.3f s, %lld IPs, range [%g, %g -> %g)%s\n", rk ? rk : "0", n_obj, t,
+                     t >= nstrips ? " (cut)" : "", slog[t].worker, slog[t].t0, slog[t].t1, slog[t].ips, slog[t].start, slog[t].stop0, slog[t].stop1,
+                     slog[t].from >= 0 ? (" cut off strip " + std::to_string(slog[t].from)).c_str() : "");
+    std::fprintf(stderr, "moip_b200: timeline rank %s level %d done after %.3f s\n", rk ? rk : "0", n_obj, since0());
+  }
   if (shared) {
     {
       std::lock_guard<std::mutex> rl(p->run_mu);

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 using namespace moip;
 
@@ -150,6 +151,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->use_points = env_int("MOIP_POINT_STORE", 1) != 0;
   c->use_fused = env_int("MOIP_FUSED_ROUND", 1) != 0;
   c->k3_poll = env_int("MOIP_K3_POLL", 1) != 0;
+  if (const char* sm = std::getenv("MOIP_SYNC")) c->block_sync = std::strcmp(sm, "block") == 0;
   {
     std::unique_lock<std::shared_mutex> lk(m->points.mu);
     if (m->points.n == 0) {
@@ -160,6 +162,20 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   }
   if (env_int("MOIP_KERNEL_TIMING", 0) && moip_ctx_set_kernel_timing(c, 1)) { moip_ctx_destroy(c); return MOIP_ERR_CUDA; }
   *out = c;
+  return MOIP_OK;
+}
+
+int moip_ctx::wait_stream() {
+  if (!block_sync) { MOIP_CUDA(cudaStreamSynchronize(stream)); return MOIP_OK; }
+  if (!sync_ev) MOIP_CUDA(cudaEventCreateWithFlags(&sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
+  MOIP_CUDA(cudaEventRecord(sync_ev, stream));
+  MOIP_CUDA(cudaEventSynchronize(sync_ev));
+  return MOIP_OK;
+}
+
+extern "C" int moip_ctx_set_sync_mode(moip_ctx* c, int blocking) {
+  if (!c) return MOIP_ERR_ARG;
+  c->block_sync = blocking != 0;
   return MOIP_OK;
 }
 
@@ -195,6 +211,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->kev) if (e) cudaEventDestroy(e);
   if (c->k3_answer) cudaFreeHost(c->k3_answer);
+  if (c->sync_ev) cudaEventDestroy(c->sync_ev);
   for (void* p : c->model_allocs) cudaFree(p);
   c->b_cost.release(); c->b_lb.release(); c->b_ub.release(); c->b_status.release(); c->b_iters.release();
   c->b_branch.release(); c->b_counter.release(); c->b_rhs.release(); c->b_pobj.release(); c->b_dbound.release();
@@ -439,6 +456,7 @@ int cache_find2(moip_ctx* c, moip_cache* s0, moip_cache* s1, int Q, const double
     c->stats.cache_queries += 1;
     volatile int* vseq = &c->k3_answer->seq;
     for (long spins = 0; *vseq != seq; ++spins) {
+      if (c->block_sync && (spins & 0x3f) == 0x3f) std::this_thread::yield();   // more workers than cores: do not hog one
       if ((spins & 0xfff) == 0xfff) {                    // a failed launch would never publish: ask the stream now and then
         const cudaError_t e = cudaStreamQuery(c->stream);
         if (e != cudaSuccess && e != cudaErrorNotReady) { MOIP_CUDA(e); }
@@ -799,7 +817,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     MOIP_CUDA(cudaMemcpyAsync(H, r_out.p, LO.end, cudaMemcpyDeviceToHost, stream));
     kmark(5);
     const double tp1 = prof ? now_s() : 0.0;
-    MOIP_CUDA(cudaStreamSynchronize(stream));
+    if (wait_stream()) return MOIP_ERR_CUDA;
     const double tp2 = prof ? now_s() : 0.0;
     if (ktiming) {
       ktimes.copy_ms += kspan(0, 1) + kspan(4, 5);

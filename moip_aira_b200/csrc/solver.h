@@ -185,6 +185,12 @@ struct moip_ctx {
   int bb_check = 32;
   int norm_every = 1;
   int bb_levels = 3;           // max tree levels expanded per round while the device is under-filled
+  // how a worker waits for its round: spinning in cudaStreamSynchronize (lowest latency, one core per worker) or sleeping on
+  // a blocking event (frees the core; ~20 us later).  MOIP_SYNC=spin|block|auto; auto blocks when the workers of all ranks
+  // on this host outnumber its cores.
+  bool block_sync = false;
+  cudaEvent_t sync_ev = nullptr;
+  int wait_stream();
   bool use_fused = true;       // register-resident K1: one fused propagate -> LP -> round/verify launch per round (MOIP_FUSED_ROUND=0: three kernels)
   bool use_points = true;      // start every IP from the best stored feasible point (PointStore); MOIP_POINT_STORE=0 disables
   long long start_hits = 0;    // IPs that began with a stored point as incumbent

@@ -41,6 +41,7 @@ cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaStreamQuery(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = (cudaEvent_t)std::malloc(8); return cudaSuccess; }
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (cudaEvent_t)std::malloc(8); return cudaSuccess; }
 cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
