@@ -168,14 +168,23 @@ class RecordExchange:
 
 # ------------------------------------------------------------------------------------ backends
 def default_workers():
-    """Solver contexts (= host threads) per GPU: MOIP_WORKERS, else up to 16 but no more than this rank's share of the
-    host's cores minus two (Python + the exchange thread).  Every worker drives its B&B rounds from its own host thread,
-    and a round costs ~40 us of CPU next to ~400 us on the device: with more workers than cores the rounds of ALL workers
-    stretch (measured on a 24-core box with 2 ranks: 16 workers per rank 5.5 s, 10 per rank 4.7 s for the 3AP n=30 front)."""
+    """Solver contexts (= host threads) per GPU: MOIP_WORKERS, else as many spinning workers as this rank's share of the
+    host's cores carries (at most 16), or -- below 8 -- 24 workers that sleep on a blocking event while their round is on
+    the device (MOIP_SYNC=auto picks the wait mode from the same numbers).  Every worker drives its B&B rounds from its own host thread: ~40 us of CPU next to
+    ~400 us on the device per round, so a sleeping worker needs a tenth of a core.  Measured, 3AP n=30 front on one B200:
+    16 cores 16 spinning workers 6.3 s; 4 cores (taskset): 4 spinning 15.8 s, 12 spinning 17.0 s, 12 / 16 / 24 sleeping
+    9.6 / 8.6 / 7.5 s (profiles/r02_fronts.md)."""
     if os.environ.get("MOIP_WORKERS"):
         return int(os.environ["MOIP_WORKERS"])
     ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    return max(4, min(16, (os.cpu_count() or 16) // ranks_here - 2))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 16
+    spare = cores // ranks_here - 2                       # Python + the exchange thread
+    if spare >= 14:
+        return 16
+    return spare if spare >= 8 else 24                    # (2 ranks on 24 cores: 10 spinning 4.7 s, 16 sleeping 5.5 s)
 
 
 class GpuBackend:

@@ -7,6 +7,8 @@
 // State per worker: rhs[k] (current bounds), hi_seen[]/lo_seen[] (the reference's max[]/min[]
 // trackers), misses (its infcnt), last_missed (inflast), level (depth_level), walking (onwalk).
 #include <algorithm>
+#include <sched.h>
+
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -577,7 +579,9 @@ extern "C" int moip_pool_create(moip_model* m, int device, int workers, moip_poo
     if (!sm || std::strcmp(sm, "auto") == 0) {
       const char* lw = std::getenv("LOCAL_WORLD_SIZE");
       const long ranks = lw ? std::max(1, std::atoi(lw)) : 1;
-      const long cores = std::max(1u, std::thread::hardware_concurrency());
+      long cores = std::max(1u, std::thread::hardware_concurrency());
+      cpu_set_t cs;                                   // the cores this process may use (taskset / cpusets), not the machine's
+      if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) cores = CPU_COUNT(&cs);
       block = (long)workers * ranks + 2 * ranks > cores;
     } else block = std::strcmp(sm, "block") == 0;
   }
@@ -745,14 +749,14 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   const bool steal = nstrips > 0 && !std::getenv("MOIP_NO_STEAL");
   int W = steal ? (int)p->ctx.size() : std::min<int>((int)p->ctx.size(), std::max(1, nstrips));
   if (p->max_workers > 0) W = std::min(W, p->max_workers);
-  const int max_strips = nstrips + (steal ? 8 * W + 64 : 0);   // (>= nstrips + max_steals below)
+  const int max_strips = nstrips + (steal ? 8 * std::max(4, W) + 64 : 0);   // (>= nstrips + max_steals below)
   std::vector<StripDyn> dyn((size_t)std::max(1, max_strips));
   std::vector<double> sstart((size_t)std::max(1, max_strips), 0.0);
   std::vector<int> cut_from((size_t)std::max(1, max_strips), -1);
   std::atomic<int> next(0), failed(0), n_dyn(nstrips), n_claiming(W), n_stolen(0);
   std::mutex steal_mu;
   // a cut must leave both halves worth a strip's start-up cost (a lower-dimensional front of its own): at least
-  // MOIP_STEAL_MIN units of the last objective (default 2) and 1/(MOIP_STEAL_FRAC W) of the level's range (default 16 W);
+  // MOIP_STEAL_MIN units of the last objective (default 2) and 1/MOIP_STEAL_FRAC of the level's range (default 1/512);
   // at most 8 W cuts per level.  An idle worker costs nothing, so the thresholds are low: the start-up of a cut-off
   // strip is paid by a worker that had nothing else to do.
   double lo_edge = HUGE_VAL, hi_edge = -HUGE_VAL;
@@ -762,10 +766,10 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
       if (std::fabs(v) < 2147483647.0) { lo_edge = std::min(lo_edge, v); hi_edge = std::max(hi_edge, v); }
     }
   const double level_range = hi_edge > lo_edge ? hi_edge - lo_edge : 0.0;
-  const double steal_frac = std::getenv("MOIP_STEAL_FRAC") ? std::atof(std::getenv("MOIP_STEAL_FRAC")) : 16.0;
+  const double steal_frac = std::getenv("MOIP_STEAL_FRAC") ? std::atof(std::getenv("MOIP_STEAL_FRAC")) : 512.0;
   const double min_steal = std::max(std::max(1.0, (double)(std::getenv("MOIP_STEAL_MIN") ? std::atoi(std::getenv("MOIP_STEAL_MIN")) : 2)),
-                                    level_range / (std::max(1.0, steal_frac) * std::max(1, W)));
-  const int max_steals = 8 * std::max(1, W);
+                                    level_range / std::max(1.0, steal_frac));
+  const int max_steals = 8 * std::max(4, W);
   // returns the index of a new strip cut off a busy one, -1 when nothing is worth cutting (yet), -2 when nothing is running
   auto try_steal = [&]() -> int {
     std::lock_guard<std::mutex> lk(steal_mu);
