@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmoip_b200.so")
-SOURCES = ["model.cpp", "capi.cpp", "generator.cpp", "solver.cu", "k1_pdhg.cu", "k1_fast.cu", "k1_small.cu", "k1_reg.cu", "k1_reg_kd2.cu", "k1_reg_kd3.cu", "k1_reg_kd4.cu", "k1_reg_kd5.cu", "k2_nodepool.cu", "k3_k4.cu"]
+SOURCES = ["model.cpp", "capi.cpp", "generator.cpp", "solver.cu", "k1_pdhg.cu", "k1_fast.cu", "k1_small.cu", "k1_reg.cu", "k1_reg_kd2.cu", "k1_reg_kd3.cu", "k1_reg_kd4.cu", "k1_reg_kd5.cu", "k2_nodepool.cu", "k3_k4.cu", "k5_chain.cu"]
 
 
 def needs_build():

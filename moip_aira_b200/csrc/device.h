@@ -99,6 +99,26 @@ struct LpBatch {
   long long* f_cand_obj;      // [B][3][k]
   unsigned char* f_cand_feas; // [B][3] structural rows satisfied
   int* f_first_free;          // [B][3] first unfixed column, its lb, ub
+  // Chained rounds (bbchain.h): the batch size and the incumbent live on the device, so that the rounds of one IP can be
+  // enqueued back to back without a host round trip in between.
+  const int* B_dev;           // non-null: the batch size is *B_dev (B is then only the grid hint of the launch)
+  int slot_base;              // no `slot` array: node b lives in row slot_base + b
+  long long* f_inc;           // non-null: min-form incumbent value; every verified candidate / leaf that beats it lowers it (atomicMin)
+  const long long* f_lim_lo;  // [k] the IP's own objective limits (f_obj_* without the incumbent cut-off): candidates must respect them
+  const long long* f_lim_hi;
+  double* f_cutoff_rw;        // == cutoff, writable: lowered together with f_inc
+};
+
+// Chained rounds (bbchain.h) for the helper kernels K2 / K4: where the batch size, the rows of the nodes and the incumbent
+// live on the device.  B_dev == nullptr: plain launch (everything in the arguments).
+struct ChainRef {
+  const int* B_dev = nullptr;        // batch size
+  int slot_base = 0;                 // node b lives in pool row slot_base + b (no ids array)
+  long long* inc = nullptr;          // min-form incumbent value, lowered with atomicMin
+  double* cutoff = nullptr;          // (double)*inc for K1
+  const int* cost = nullptr;         // optimised objective
+  const long long* lim_lo = nullptr; // [k] the IP's own objective limits
+  const long long* lim_hi = nullptr;
 };
 
 struct LpParams {
@@ -168,7 +188,8 @@ int launch_k3_one(const DevCache& c0, const DevCache& c1, const K3Query& q, int 
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub,
                     int* xr /*[B][3][n]*/, long long* obj_out /*[B][3][k]*/, unsigned char* feasible_out /*[B][3]*/,
                     int* first_free /*[B][3]: first unfixed column, its lb, ub (or nullptr)*/,
-                    const int* skip /*[B] nonzero: node decided by K2, not rounded (or nullptr)*/, cudaStream_t st);
+                    const int* skip /*[B] nonzero: node decided by K2, not rounded (or nullptr)*/, cudaStream_t st,
+                    const ChainRef& ch = ChainRef());
 // Largest grid of the short per-round helper kernels (K2 propagate / K4 round).  Their CTAs are latency-bound and each
 // one that lands on an SM holds registers a K1 CTA of another worker could use (K1: 2 CTAs x 32 K registers fill an SM),
 // so they are kept on few SMs and loop over the nodes instead of spreading one CTA per node (MOIP_AUX_GRID overrides).

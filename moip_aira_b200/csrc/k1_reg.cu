@@ -12,7 +12,7 @@ int launch_k1_reg_kd5(const DevModel&, const LpBatch&, const LpParams&, int, cud
 
 int launch_k1_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (b.B <= 0) return MOIP_OK;
-  MOIP_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(int), st));
+  if (!b.B_dev) MOIP_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(int), st));   // (chained rounds: K5 resets it)
   switch (dm.KD) {
     case 2: return launch_k1_reg_kd2(dm, b, p, num_sms, st);
     case 3: return launch_k1_reg_kd3(dm, b, p, num_sms, st);

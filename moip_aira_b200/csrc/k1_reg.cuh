@@ -146,7 +146,9 @@ enum : unsigned { ROLE_ELL = 1u, ROLE_DENSE = 2u, ROLE_NORM = 4u, ROLE_LEADER = 
 constexpr int kYshBytes = 2048;            // ysh[256]   current dual iterate, published for the column pass
 constexpr int kProdBase = kYshBytes;       // prod[msS*RWP + 2] products S_ij * xbar_j (+ dummy slot)
 constexpr int kDL = 16;                    // lanes that add up one dense row / one norm
-enum { COLD_BEST_LB = 0, COLD_POBJ, COLD_DOBJ, COLD_OBJ_UPPER, COLD_KKT_BINV, COLD_W, COLD_R0SQ, COLD_RPREV, COLD_N = 8 };
+enum { COLD_BEST_LB = 0, COLD_POBJ, COLD_DOBJ, COLD_OBJ_UPPER, COLD_KKT_BINV, COLD_W, COLD_R0SQ, COLD_RPREV, COLD_CUTOFF, COLD_N = 10 };
+
+__device__ __forceinline__ int cost_of(const LpBatch& b, int node) { return b.cost_idx[(size_t)node * b.cost_stride]; }
 
 // FUSED: the B&B instantiation (LpBatch::fused): K2 propagation in front of the LP, K4 rounding/verification behind it.
 // The plain instantiation (batch API, bench `value`) carries none of that code, so its iteration loop keeps its registers.
@@ -172,6 +174,10 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
   double* xas = xts + NT * CPT;                              // [CPT][NT] thread-private Halpern anchor
   double* part = xas + NT * CPT;                             // [NV][NT]  per-thread partial sums of the dense rows / norms
   __shared__ int s_prop[FUSED ? 4 : 1];                      // flags of the fused propagation
+  // chained rounds: the batch size comes from the device; with dynamic scheduling the first batchB CTAs take every node,
+  // so the others leave before they load the model
+  const int batchB = (FUSED && b.B_dev) ? *b.B_dev : b.B;
+  if (FUSED && (int)blockIdx.x >= batchB) return;
   const int tid = threadIdx.x, lane = tid & 31;
   const int LPR = 1 << lpr_log2;
   // ---- roles in the row phase: LPR lanes per short structural row from thread 0 up, one half-warp per dense
@@ -258,8 +264,8 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
     if (tid == 0) s_node[0] = atomicAdd(b.work_counter, 1);
     __syncthreads();
     const int node = s_node[0];
-    if (node >= b.B) break;
-    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)node;   // row of the node's arrays
+    if (node >= batchB) break;
+    const size_t srow = b.slot ? (size_t)b.slot[node] : (size_t)(b.slot_base + node);   // row of the node's arrays
     if (FUSED) {
       // ---- fused round, part 1: K2 propagation of this node (xts|xas hold the 4n ints, part the per-warp partial sums)
       const int f = k2::propagate_node<NT>(dm, b.lb + srow * n, b.ub + srow * n, b.f_obj_lo, b.f_obj_hi, b.f_max_rounds,
@@ -267,7 +273,13 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
                                            b.f_leaf_obj + (size_t)node * k);
       if (tid == 0) b.f_flag[node] = f;
       if (f != 0) {                                           // infeasible or leaf: nothing to solve
-        if (tid == 0) { b.status[node] = -1; b.iters[node] = 0; }
+        if (tid == 0) {
+          b.status[node] = -1; b.iters[node] = 0;
+          if (f == 2 && b.f_inc) {                            // a leaf is a verified point: it may be the new incumbent
+            const long long v = (long long)dm.sgn * b.f_leaf_obj[(size_t)node * k + cost_of(b, node)];
+            if (v < atomicMin(b.f_inc, v)) *b.f_cutoff_rw = (double)v;
+          }
+        }
         __syncthreads();
         continue;
       }
@@ -494,6 +506,9 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
           const double viol = dmax(0.0, dmax(r_sxt + r_nhi, -r_nlo - r_sxt)) / dm.dr_k[row];
           aC[3] = viol * viol;
         }
+        // chained rounds: other CTAs lower the cutoff while this one runs -- one thread reads it, so that every thread of
+        // the CTA takes the same way out of the loop
+        if (FUSED && tid == 0) cold[COLD_CUTOFF] = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
         bsum<6, NT>(aC, redC, tid);
         const double pobj = aC[0], dobj = aC[1] + aC[2];
         // Farkas certificate: F(y) = min over the box of (-S^T y) x + (y+ lo - y- hi) <= 0 for every point that satisfies
@@ -507,7 +522,7 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
           if (dobj > best_lb) best_lb = dobj;
           const double gap = fabs(pobj - dobj);
           const double rel = dmax(sqrt(aC[3]) * kkt_binv, gap / (1.0 + fabs(pobj) + fabs(dobj)));
-          const double cutoff = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
+          const double cutoff = FUSED ? cold[COLD_CUTOFF] : (b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL);
           if (best_lb >= cutoff - p.cutoff_slack) { status = MOIP_LP_CUTOFF; stop = true; }
           else if (farkas || best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
           else if (rel <= p.eps) { status = MOIP_LP_CONVERGED; stop = true; }
@@ -704,6 +719,22 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
         b.f_first_free[(size_t)node * 3 + 1] = f1 == INT_MAX ? 0 : b.lb[srow * n + f1];
         b.f_first_free[(size_t)node * 3 + 2] = f1 == INT_MAX ? 0 : b.ub[srow * n + f1];
       }
+      if (b.f_inc) {                                          // chained rounds: the incumbent value is kept on the device
+        __syncthreads();                                      // the candidates' objective values are in global memory
+        if (tid == 0) {
+          long long best = LLONG_MAX;
+          for (int md = 0; md < 3; ++md) {
+            if (!b.f_cand_feas[(size_t)node * 3 + md]) continue;
+            const long long* ov = b.f_cand_obj + ((size_t)node * 3 + md) * k;
+            bool ok = true;
+            for (int o = 0; o < k; ++o) ok = ok && ov[o] >= b.f_lim_lo[o] && ov[o] <= b.f_lim_hi[o];
+            const long long v = (long long)dm.sgn * ov[cost];
+            if (ok && v < best) best = v;
+          }
+          // (a stale, larger cutoff left by a racing writer is still valid: it is only ever compared against bounds)
+          if (best != LLONG_MAX && best < atomicMin(b.f_inc, best)) *b.f_cutoff_rw = (double)best;
+        }
+      }
     }
     if (tid == 0) {
       b.primal_obj[node] = pobj;
@@ -760,7 +791,7 @@ int launch_reg_f(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, 
 template <int NT, int CPT, int KD, int ELLW, int MINB>
 int launch_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (b.fused) {
-    if (!b.slot) return MOIP_ERR_ARG;
+    if (!b.slot && !b.B_dev) return MOIP_ERR_ARG;
     return launch_reg_f<NT, CPT, KD, ELLW, MINB, true>(dm, b, p, num_sms, st);
   }
   return launch_reg_f<NT, CPT, KD, ELLW, MINB, false>(dm, b, p, num_sms, st);

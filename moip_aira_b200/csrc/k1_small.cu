@@ -96,6 +96,7 @@ k1_small_kernel(const DevModel dm, const LpBatch b, const LpParams p) {
   // row state (per lane: the row this lane owns)
   double r_nlo = HUGE_VAL, r_nhi = -HUGE_VAL, r_y = 0, r_ya = 0, r_sx = 0, r_sxa = 0, r_yt = 0, r_sxt = 0;
   const int iter_cap = p.fixed_iters > 0 ? p.fixed_iters : p.max_iter;
+  const int batchB = b.B_dev ? *b.B_dev : b.B;          // chained rounds: the batch size lives on the device
 
   for (;;) {
     // ================================================================ node load
@@ -104,19 +105,19 @@ k1_small_kernel(const DevModel dm, const LpBatch b, const LpParams p) {
       if (need_load && gl == 0) {
         for (;;) {
           nd = atomicAdd(b.work_counter, 1);
-          if (nd >= b.B || !(b.skip && b.skip[nd])) break;
+          if (nd >= batchB || !(b.skip && b.skip[nd])) break;
           b.status[nd] = -1; b.iters[nd] = 0;            // already decided by K2
         }
       }
       nd = __shfl_sync(kFull, nd, gbase);
-      const bool ld = need_load && nd < b.B;
-      if (need_load && nd >= b.B) alive = false;
+      const bool ld = need_load && nd < batchB;
+      if (need_load && nd >= batchB) alive = false;
       need_load = false;
       unsigned act = 0;
       const double* nrhs = b.rhs;
       if (ld) {
         node = nd;
-        srow = b.slot ? (size_t)b.slot[node] : (size_t)node;
+        srow = b.slot ? (size_t)b.slot[node] : (size_t)(b.slot_base + node);
         cost = b.cost_idx[(size_t)node * b.cost_stride];
         nrhs = b.rhs + (size_t)node * b.rhs_stride;
         inv_dr_cost = 1.0 / dm.dr_k[cost];
@@ -312,6 +313,9 @@ k1_small_kernel(const DevModel dm, const LpBatch b, const LpParams p) {
       const double pobj = shi(s, gbase), dobj = shi(s, gbase + 1) + shi(s, gbase + 2), pres2 = shi(s, gbase + 3);
       // Farkas certificate (see k1_reg.cuh): F(y) > 0 proves the node LP infeasible
       const bool farkas = shi(s, gbase + 4) + shi(s, gbase + 2) > 1e-9 * shi(s, gbase + 5) + 1e-9;
+      // one lane reads the cutoff for its group: with chained rounds other CTAs lower it while this one runs, and the 8
+      // lanes of a node must take the same way out
+      const double cutoff_g = shi(b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL, gbase);
       if (eval_it) {
         if (check_it) next_check += p.check_every;
         double best_lb = cold_g[COLD_BEST_LB];
@@ -321,7 +325,7 @@ k1_small_kernel(const DevModel dm, const LpBatch b, const LpParams p) {
           if (dobj > best_lb) best_lb = dobj;
           const double gap = fabs(pobj - dobj);
           const double rel = dmax(sqrt(pres2) * kkt_binv, gap / (1.0 + fabs(pobj) + fabs(dobj)));
-          const double cutoff = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
+          const double cutoff = cutoff_g;
           if (best_lb >= cutoff - p.cutoff_slack) { status = MOIP_LP_CUTOFF; stop = true; }
           else if (farkas || best_lb > obj_upper + 1e-6 * (1.0 + fabs(obj_upper))) { status = MOIP_LP_INFEASIBLE; stop = true; }
           else if (rel <= p.eps) { status = MOIP_LP_CONVERGED; stop = true; }
@@ -480,7 +484,7 @@ bool k1_small_applies(const DevModel& dm) {
 
 int launch_k1_small(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (b.B <= 0) return MOIP_OK;
-  MOIP_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(int), st));
+  if (!b.B_dev) MOIP_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(int), st));   // (chained rounds: K5 resets it)
   switch (dm.KD) {
     case 3: return launch_small_kd<3>(dm, b, p, num_sms, st);
     case 4: return launch_small_kd<4>(dm, b, p, num_sms, st);

@@ -21,15 +21,22 @@ constexpr int kPropThreads = 256;
 __global__ void __launch_bounds__(kPropThreads) k2_propagate_kernel(const DevModel dm, const PoolView pool, int B,
                                                                     const int* ids, const long long* obj_lo,
                                                                     const long long* obj_hi, int max_rounds, int* flag,
-                                                                    long long* leaf_obj) {
+                                                                    long long* leaf_obj, const ChainRef ch) {
   extern __shared__ int sm_i[];
   __shared__ int s_flags[4];
   __shared__ long long s_act[(kPropThreads / 32) * 2 * MOIP_MAX_OBJ];
+  if (ch.B_dev) B = *ch.B_dev;
   for (int bi = blockIdx.x; bi < B; bi += gridDim.x) {
-    const int slot = ids[bi];
+    const int slot = ch.B_dev ? ch.slot_base + bi : ids[bi];
     const int f = k2::propagate_node<kPropThreads>(dm, pool.lb + (size_t)slot * dm.n, pool.ub + (size_t)slot * dm.n, obj_lo, obj_hi,
                                                    max_rounds, sm_i, s_act, s_flags, leaf_obj + (size_t)bi * dm.k);
-    if (threadIdx.x == 0) flag[bi] = f;
+    if (threadIdx.x == 0) {
+      flag[bi] = f;
+      if (f == 2 && ch.inc) {              // a leaf is a verified point: it may be the new incumbent (chained rounds)
+        const long long v = (long long)dm.sgn * leaf_obj[(size_t)bi * dm.k + *ch.cost];
+        if (v < atomicMin(ch.inc, v)) *ch.cutoff = (double)v;
+      }
+    }
   }
 }
 
@@ -61,7 +68,8 @@ __global__ void __launch_bounds__(128) k2_branch_kernel(const DevModel dm, const
 }  // namespace
 
 int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const int* ids, const long long* obj_lo,
-                        const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st) {
+                        const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st,
+                        const ChainRef& ch) {
   if (B <= 0) return MOIP_OK;
   const size_t smem = sizeof(int) * 4 * (size_t)dm.n;
   static LaunchCfg cfg;
@@ -76,7 +84,7 @@ int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const i
   if (set_aux_carveout(k2_propagate_kernel, carve)) return MOIP_ERR_CUDA;
   const int gcap = aux_grid_cap();
   int grid = B < gcap ? B : gcap;
-  k2_propagate_kernel<<<grid, kPropThreads, smem, st>>>(dm, pool, B, ids, obj_lo, obj_hi, max_rounds, flag, leaf_obj);
+  k2_propagate_kernel<<<grid, kPropThreads, smem, st>>>(dm, pool, B, ids, obj_lo, obj_hi, max_rounds, flag, leaf_obj, ch);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }

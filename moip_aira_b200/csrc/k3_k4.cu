@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(128) k4_verify_kernel(const DevModel dm, int B
 // each candidate exactly; one warp per (node, candidate).  Feeds the incumbent search of the B&B.
 __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm, int B, const int* slot, const double* wx,
                                                               const int* lb, const int* ub, int* xr, long long* obj_out,
-                                                              unsigned char* feasible_out, int* first_free, const int* skip) {
+                                                              unsigned char* feasible_out, int* first_free, const int* skip,
+                                                              const ChainRef ch) {
+  if (ch.B_dev) B = *ch.B_dev;
   const int lane = threadIdx.x & 31;
   const int wglobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
   for (int w = wglobal; w < B * 3; w += nwarps) {
     const int node = w / 3, mode = w - node * 3;
     if (skip && skip[node]) continue;      // decided by K2 (infeasible / leaf): nobody reads its roundings
-    const size_t srow = slot ? (size_t)slot[node] : (size_t)node;
+    const size_t srow = slot ? (size_t)slot[node] : (size_t)(ch.slot_base + node);
     int* xp = xr + (size_t)w * n;
     long long obj[MOIP_MAX_OBJ] = {0, 0, 0, 0};
     int ff = INT_MAX;                     // first column that is not fixed yet (fallback branching column)
@@ -220,6 +222,17 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
     if (lane == 0) {
       feasible_out[w] = bad ? 0 : 1;
       for (int o = 0; o < dm.k; ++o) obj_out[(size_t)w * dm.k + o] = obj[o];
+      if (ch.inc && !bad) {                  // chained rounds: a verified candidate within the IP's limits may be the new incumbent
+        bool ok = true;
+#pragma unroll
+        for (int o = 0; o < MOIP_MAX_OBJ; ++o)
+          if (o < dm.k) ok = ok && obj[o] >= ch.lim_lo[o] && obj[o] <= ch.lim_hi[o];
+        long long v = 0;
+        const int cost = *ch.cost;
+#pragma unroll
+        for (int o = 0; o < MOIP_MAX_OBJ; ++o) if (o == cost) v = (long long)dm.sgn * obj[o];
+        if (ok && v < atomicMin(ch.inc, v)) *ch.cutoff = (double)v;
+      }
     }
   }
 }
@@ -227,14 +240,15 @@ __global__ void __launch_bounds__(128) k4_round_verify_kernel(const DevModel dm,
 }  // namespace
 
 int launch_k4_round(const DevModel& dm, int B, const int* slot, const double* wx, const int* lb, const int* ub, int* xr,
-                    long long* obj_out, unsigned char* feasible_out, int* first_free, const int* skip, cudaStream_t st) {
+                    long long* obj_out, unsigned char* feasible_out, int* first_free, const int* skip, cudaStream_t st,
+                    const ChainRef& ch) {
   if (B <= 0) return MOIP_OK;
   int blocks = (B * 3 + 3) / 4;
   static LaunchCfg carve;
   if (set_aux_carveout(k4_round_verify_kernel, carve)) return MOIP_ERR_CUDA;
   const int cap = aux_grid_cap();
   if (blocks > cap) blocks = cap;
-  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out, first_free, skip);
+  k4_round_verify_kernel<<<blocks, 128, 0, st>>>(dm, B, slot, wx, lb, ub, xr, obj_out, feasible_out, first_free, skip, ch);
   MOIP_CUDA(cudaGetLastError());
   return MOIP_OK;
 }

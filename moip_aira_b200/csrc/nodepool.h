@@ -18,7 +18,8 @@ struct BranchOp {           // child = copy of parent with up to 3 columns tight
 };
 
 int launch_k2_propagate(const DevModel& dm, const PoolView& pool, int B, const int* ids, const long long* obj_lo,
-                        const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st);
+                        const long long* obj_hi, int max_rounds, int* flag, long long* leaf_obj, cudaStream_t st,
+                        const ChainRef& ch = ChainRef());
 int launch_k2_branch(const DevModel& dm, const PoolView& pool, int C, const BranchOp* ops, cudaStream_t st);
 
 }  // namespace moip

@@ -150,6 +150,9 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->bb_levels = env_int("MOIP_BB_LEVELS", 3);
   c->use_points = env_int("MOIP_POINT_STORE", 1) != 0;
   c->use_fused = env_int("MOIP_FUSED_ROUND", 1) != 0;
+  c->use_chain = env_int("MOIP_CHAIN", 1) != 0;
+  c->chain_q = std::max(64, env_int("MOIP_CHAIN_Q", 4096));
+  c->chain_debug = env_int("MOIP_CHAIN_DEBUG", 0) != 0;
   c->k3_poll = env_int("MOIP_K3_POLL", 1) != 0;
   if (const char* sm = std::getenv("MOIP_SYNC")) c->block_sync = std::strcmp(sm, "block") == 0;
   {
@@ -207,6 +210,16 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
                      sg, sg == MOIP_MAX_OBJ ? " (get_limit / mip_solve)" : "", c->stage_ips[sg], (double)c->stage_nodes[sg] / c->stage_ips[sg],
                      (double)c->stage_lps[sg] / c->stage_ips[sg], (double)c->stage_rounds[sg] / c->stage_ips[sg],
                      100.0 * c->stage_root_solved[sg] / c->stage_ips[sg], sg == 0 ? c->start_hits : 0LL);
+  if (c->chain_ips > 0 && std::getenv("MOIP_CHAIN_STATS")) {
+    std::fprintf(stderr, "moip_b200: chained rounds: %lld IPs, %.2f host waits and %.2f idle rounds per IP, %lld handed back to the host loop; node-LP cap %d\n",
+                 c->chain_ips, (double)c->chain_chunks / c->chain_ips, (double)c->chain_idle_rounds / c->chain_ips, c->chain_fallbacks,
+                 c->bb_max_iter > 0 ? c->bb_max_iter : c->lp_cap_dyn);
+    for (int sg = 0; sg <= MOIP_MAX_OBJ; ++sg)
+      if (c->stage_ips[sg])
+        std::fprintf(stderr, "moip_b200:   stage %d: %lld IPs, %.1f nodes, %.1f node LPs, %.2f rounds per IP; %.0f %% done after the root round\n",
+                     sg, c->stage_ips[sg], (double)c->stage_nodes[sg] / c->stage_ips[sg], (double)c->stage_lps[sg] / c->stage_ips[sg],
+                     (double)c->stage_rounds[sg] / c->stage_ips[sg], 100.0 * c->stage_root_solved[sg] / c->stage_ips[sg]);
+  }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->kev) if (e) cudaEventDestroy(e);
@@ -221,6 +234,7 @@ extern "C" void moip_ctx_destroy(moip_ctx* c) {
   c->p_lb.release(); c->p_ub.release(); c->p_wx.release(); c->p_wy.release();
   c->r_xr.release(); c->r_counter.release(); c->r_pobj.release();
   c->r_ops.release(); c->h_round.release(); c->r_in.release(); c->r_out.release(); c->h_in.release(); c->h_ops.release(); c->d_inc.release(); c->d_root_x.release(); c->d_root_y.release(); c->k1_scratch.release();
+  c->d_ctl.release(); c->h_ctl.release(); c->h_inc.release(); c->c_bound.release(); c->c_depth.release();
   if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -619,6 +633,144 @@ struct OpenNode {
 };
 }  // namespace
 
+// One IP with its rounds chained on the device (bbchain.h).  The host enqueues a chunk of rounds -- node LPs with the fused
+// propagation / rounding (k1_reg.cuh) followed by K5 (k5_chain.cu) -- copies the control block back and waits once per
+// chunk; the first chunk is as long as this stage's IPs usually need.  Same exactness model as the host loop below: int64
+// propagation and verification, pruning on valid Lagrangian bounds only.
+int moip_ctx::solve_ip_chained(int cost, const double* srhs, const long long* olo, const long long* ohi, bool& have_inc,
+                               long long& inc_val, std::vector<int>& inc_x, bool& handled) {
+  handled = false;
+  const Model& M = model->M;
+  const int n = dm.n, k = dm.k, m = dm.m;
+  const int Q = chain_q;
+  int rc = 0;
+  if (ensure_pool(2 * Q)) return MOIP_ERR_CUDA;
+  auto up8 = [](size_t v) { return (v + 7) & ~(size_t)7; };
+  struct OutLayout { size_t flag, status, iters, branch, ff, dbound, bval, leaf, cobj, cfeas, end; } LO;
+  LO.flag = 0; LO.status = up8(LO.flag + sizeof(int) * Q); LO.iters = up8(LO.status + sizeof(int) * Q);
+  LO.branch = up8(LO.iters + sizeof(int) * Q); LO.ff = up8(LO.branch + sizeof(int) * 3 * Q);
+  LO.dbound = up8(LO.ff + sizeof(int) * 3 * Q);
+  LO.bval = LO.dbound + sizeof(double) * Q; LO.leaf = LO.bval + sizeof(double) * 3 * Q;
+  LO.cobj = LO.leaf + sizeof(long long) * Q * k; LO.cfeas = LO.cobj + sizeof(long long) * Q * 3 * k;
+  LO.end = up8(LO.cfeas + (size_t)Q * 3);
+  rc |= r_out.ensure(LO.end); rc |= r_xr.ensure((size_t)Q * 3 * n); rc |= r_pobj.ensure(Q);
+  rc |= d_inc.ensure(n); rc |= d_root_x.ensure((size_t)k * n); rc |= d_root_y.ensure((size_t)k * m);
+  rc |= d_ctl.ensure(1); rc |= h_ctl.ensure(1); rc |= h_inc.ensure(n); rc |= c_bound.ensure((size_t)2 * Q); rc |= c_depth.ensure((size_t)2 * Q);
+  if (rc) return MOIP_ERR_CUDA;
+  const PoolView pool{p_lb.p, p_ub.p, p_wx.p, p_wy.p};
+  BbCtl* ctl = d_ctl.p;
+  const int Bmax = bb_batch > 0 ? bb_batch : num_sms * (dm.n <= 64 ? 16 : 4);
+  const bool fused = dm.reg_ok;          // register-resident K1: K2 and K4 run inside its CTAs; else (8-lanes-per-node K1) as kernels of their own
+
+  const bool cold_root = !root_valid[cost];
+  if (lp_cap_dyn <= 0) lp_cap_dyn = std::min(2000, std::max(200, (int)(20.0 * std::sqrt((double)n))));
+  const int lp_cap = bb_max_iter > 0 ? bb_max_iter : lp_cap_dyn;
+  LpParams lp{};
+  lp.eps = bb_eps; lp.check_every = bb_check; lp.fixed_iters = 0;
+  lp.norm_every = norm_every > 0 ? norm_every : 1; lp.cutoff_slack = 1.0 - 1e-6; lp.int_obj = 1;
+
+  BbInit init{};
+  for (int o = 0; o < MOIP_MAX_OBJ; ++o) {
+    init.olo[o] = o < k ? olo[o] : LLONG_MIN; init.ohi[o] = o < k ? ohi[o] : LLONG_MAX; init.rhs[o] = o < k ? srhs[o] : 0.0;
+  }
+  const long long inc0 = have_inc ? inc_val : LLONG_MAX;
+  init.inc_val = inc0; init.cost = cost; init.sense = M.sense; init.qcap = Q; init.bmax = Bmax;
+  init.levels_max = std::max(1, bb_levels); init.warm = cold_root ? 0 : 1;
+  init.root_x = d_root_x.p + (size_t)cost * n; init.root_y = d_root_y.p + (size_t)cost * m;
+  if (launch_bb_init(dm, pool, ctl, init, c_bound.p, c_depth.p, stream)) return MOIP_ERR_CUDA;
+
+  BbRound R{};
+  R.cold_root = cold_root ? 1 : 0;
+  R.flag = reinterpret_cast<const int*>(r_out.p + LO.flag); R.status = reinterpret_cast<const int*>(r_out.p + LO.status);
+  R.iters = reinterpret_cast<const int*>(r_out.p + LO.iters); R.branch = reinterpret_cast<const int*>(r_out.p + LO.branch);
+  R.bval = reinterpret_cast<const double*>(r_out.p + LO.bval); R.ff = reinterpret_cast<const int*>(r_out.p + LO.ff);
+  R.dbound = reinterpret_cast<const double*>(r_out.p + LO.dbound); R.leaf = reinterpret_cast<const long long*>(r_out.p + LO.leaf);
+  R.cobj = reinterpret_cast<const long long*>(r_out.p + LO.cobj); R.cfeas = r_out.p + LO.cfeas; R.xr = r_xr.p;
+  R.node_bound = c_bound.p; R.node_depth = c_depth.p; R.inc_x = d_inc.p;
+  R.root_x = d_root_x.p + (size_t)cost * n; R.root_y = d_root_y.p + (size_t)cost * m;
+
+  LpBatch b{};
+  b.rhs = ctl->rhs; b.lb = pool.lb; b.ub = pool.ub; b.slot = nullptr; b.rc_fix = 1;
+  b.fused = fused ? 1 : 0; b.f_obj_lo = ctl->plo; b.f_obj_hi = ctl->phi; b.f_max_rounds = 16;
+  b.f_flag = reinterpret_cast<int*>(r_out.p + LO.flag); b.f_leaf_obj = reinterpret_cast<long long*>(r_out.p + LO.leaf);
+  b.f_xr = r_xr.p; b.f_cand_obj = reinterpret_cast<long long*>(r_out.p + LO.cobj); b.f_cand_feas = r_out.p + LO.cfeas;
+  b.f_first_free = reinterpret_cast<int*>(r_out.p + LO.ff);
+  b.warm_x = pool.wx; b.warm_y = pool.wy; b.out_x = pool.wx; b.out_y = pool.wy;
+  b.primal_obj = r_pobj.p; b.dual_bound = reinterpret_cast<double*>(r_out.p + LO.dbound);
+  b.status = reinterpret_cast<int*>(r_out.p + LO.status); b.iters = reinterpret_cast<int*>(r_out.p + LO.iters);
+  b.branch_var = reinterpret_cast<int*>(r_out.p + LO.branch); b.branch_val = reinterpret_cast<double*>(r_out.p + LO.bval);
+  b.skip = fused ? nullptr : b.f_flag; b.cost_stride = 0; b.rhs_stride = 0; b.cost_idx = &ctl->cost;
+  b.cutoff = &ctl->cutoff; b.f_cutoff_rw = &ctl->cutoff; b.work_counter = &ctl->work_counter;
+  b.f_inc = &ctl->inc_val; b.f_lim_lo = ctl->olo; b.f_lim_hi = ctl->ohi;
+  ChainRef ch;
+  ch.inc = &ctl->inc_val; ch.cutoff = &ctl->cutoff; ch.cost = &ctl->cost; ch.lim_lo = ctl->olo; ch.lim_hi = ctl->ohi;
+
+  dbg_where.store(2, std::memory_order_relaxed);
+  const int stage = cur_stage;
+  int chunk = std::min(16, std::max(2, (int)std::ceil(chain_rounds_avg[stage] + 0.5)));
+  int r = 0;
+  const BbCtl* H = h_ctl.p;
+  for (;;) {
+    for (int c = 0; c < chunk; ++c, ++r) {
+      const int p = r & 1;
+      const int hint = r < 4 ? std::min(Q, 1 << (3 * r)) : Q;          // a level is at most 8 times the one before
+      b.B = hint; b.B_dev = &ctl->count[p]; b.slot_base = p * Q;
+      lp.max_iter = (r == 0 && cold_root) ? std::max(lp_cap, 20000) : lp_cap;
+      ch.B_dev = b.B_dev; ch.slot_base = b.slot_base;
+      if (!fused && launch_k2_propagate(dm, pool, hint, nullptr, ctl->plo, ctl->phi, 16, b.f_flag, b.f_leaf_obj, stream, ch)) return MOIP_ERR_CUDA;
+      if (launch_k1_any(dm, b, lp, num_sms, stream)) return MOIP_ERR_CUDA;
+      if (!fused && launch_k4_round(dm, hint, nullptr, pool.wx, pool.lb, pool.ub, r_xr.p, b.f_cand_obj, b.f_cand_feas, b.f_first_free,
+                                    b.f_flag, stream, ch)) return MOIP_ERR_CUDA;
+      if (chain_debug) {
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { std::fprintf(stderr, "moip_b200: chained round %d: K1 failed: %s (n=%d cost=%d cold=%d cap=%d)\n", r, cudaGetErrorString(e), n, cost, (int)cold_root, lp.max_iter); return MOIP_ERR_CUDA; }
+      }
+      R.parity = p; R.round = r;
+      if (launch_bb_advance(dm, pool, ctl, R, hint, stream)) return MOIP_ERR_CUDA;
+      if (chain_debug) {
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) { std::fprintf(stderr, "moip_b200: chained round %d: K5 failed: %s (n=%d)\n", r, cudaGetErrorString(e), n); return MOIP_ERR_CUDA; }
+      }
+    }
+    stats.kernel_launches += (fused ? 2 : 4) * chunk;
+    chain_chunks += 1;
+    MOIP_CUDA(cudaMemcpyAsync(h_ctl.p, ctl, sizeof(BbCtl), cudaMemcpyDeviceToHost, stream));
+    MOIP_CUDA(cudaMemcpyAsync(h_inc.p, d_inc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+    if (wait_stream()) return MOIP_ERR_CUDA;
+    dbg_rounds.store(r, std::memory_order_relaxed); dbg_open.store(H->count[r & 1], std::memory_order_relaxed);
+    if (H->overflow || H->count[r & 1] == 0) break;
+    chunk = 3;
+  }
+  // ---- what the device did
+  stats.bb_nodes += (long long)H->n_nodes; stage_nodes[stage] += (long long)H->n_nodes;
+  stats.node_lps += (long long)H->n_lps; stage_lps[stage] += (long long)H->n_lps;
+  stats.lp_iterations += (long long)H->n_iters;
+  stage_rounds[stage] += H->rounds_live;
+  if (H->rounds_live <= 1) stage_root_solved[stage] += 1;
+  chain_ips += 1; chain_idle_rounds += r - H->rounds_live;
+  if (H->root_solved) root_valid[cost] = 1;
+  cap_seen += (long long)H->n_solved; cap_hit += (long long)H->n_capped;
+  prof_t[5] += (double)H->n_solved; prof_t[6] += (double)H->n_capped;
+  if (bb_max_iter <= 0 && cap_seen >= 64) {       // cap controller (see the host loop): once per IP here
+    const double share = (double)cap_hit / (double)cap_seen;
+    if (share > bb_cap_hi) lp_cap_dyn = std::min(6000, lp_cap_dyn + lp_cap_dyn / 4 + 1);
+    else if (share < bb_cap_lo) lp_cap_dyn = std::max(100, lp_cap_dyn - lp_cap_dyn / 8);
+    cap_seen = 0; cap_hit = 0;
+  }
+  if (H->inc_val < inc0) {
+    if (H->inc_seen != H->inc_val) {
+      std::fprintf(stderr, "moip_b200: chained rounds lost the incumbent's point (value %lld, point of %lld)\n", H->inc_val, H->inc_seen);
+      return MOIP_ERR_CUDA;
+    }
+    have_inc = true; inc_val = H->inc_val;
+    inc_x.assign(h_inc.p, h_inc.p + n);
+  }
+  if (H->overflow) { chain_fallbacks += 1; return MOIP_OK; }      // the caller's loop solves the IP from the root, with this incumbent
+  chain_rounds_avg[stage] += 0.125 * ((double)H->rounds_live - chain_rounds_avg[stage]);
+  handled = true;
+  return MOIP_OK;
+}
+
 // One single-objective IP:  optimise objective `cost` s.t. the structural rows and C x (<=|>=) srhs.
 // Exactness: pruning uses only valid Lagrangian bounds from K1 and int64 propagation from K2;
 // incumbents are accepted only after exact int64 evaluation (K2 leaves / K4 rounded LP points).
@@ -655,6 +807,35 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     if (model->points.best(cost, (long long)sgn, olo.data(), ohi.data(), have_inc ? inc_val : LLONG_MAX, inc_x, v)) {
       have_inc = true; inc_val = v; start_hits += 1;
     }
+  }
+  // what every way out of this function does with the incumbent
+  auto finish = [&](bool inc_on_device) -> int {
+    if (!have_inc) return MOIP_OK;
+    if (inc_on_device) {
+      inc_x.resize(n);
+      MOIP_CUDA(cudaMemcpyAsync(inc_x.data(), d_inc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
+      MOIP_CUDA(cudaStreamSynchronize(stream));
+    }
+    out.status = MOIP_MIP_OPTIMAL;
+    out.obj = (long long)sgn * inc_val;
+    out.x = inc_x;
+    if (use_points) {
+      long long ov[MOIP_MAX_OBJ] = {0, 0, 0, 0};
+      for (int o = 0; o < k; ++o) {
+        long long v = 0;
+        const int64_t* co = M.ci.data() + (size_t)o * n;
+        for (int j = 0; j < n; ++j) v += co[j] * (long long)inc_x[j];
+        ov[o] = v;
+      }
+      model->points.add(inc_x.data(), ov);
+    }
+    return MOIP_OK;
+  };
+  // chained rounds: the tree advances on the device; the host loop below only takes over when a level outgrows the pool
+  if (use_chain && ((use_fused && dm.reg_ok) || (!dm.reg_ok && k1_small_applies(dm))) && !ktiming && !std::getenv("MOIP_PROFILE_ROUNDS")) {
+    bool handled = false;
+    if (int rcc = solve_ip_chained(cost, srhs, olo.data(), ohi.data(), have_inc, inc_val, inc_x, handled)) return rcc;
+    if (handled) { dbg_where.store(0, std::memory_order_relaxed); return finish(false); }
   }
   // batch geometry
   int Bmax = bb_batch > 0 ? bb_batch : num_sms * (dm.n <= 64 ? 16 : 4);
@@ -953,27 +1134,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   for (auto& nd : open) free_slots.push_back(nd.slot);
   dbg_where.store(0, std::memory_order_relaxed);
   if (ip_rounds <= 1) stage_root_solved[cur_stage] += 1;
-  if (have_inc) {
-    if (inc_on_device) {
-      inc_x.resize(n);
-      MOIP_CUDA(cudaMemcpyAsync(inc_x.data(), d_inc.p, sizeof(int) * n, cudaMemcpyDeviceToHost, stream));
-      MOIP_CUDA(cudaStreamSynchronize(stream));
-    }
-    out.status = MOIP_MIP_OPTIMAL;
-    out.obj = (long long)sgn * inc_val;
-    out.x = inc_x;
-    if (use_points) {
-      long long ov[MOIP_MAX_OBJ] = {0, 0, 0, 0};
-      for (int o = 0; o < k; ++o) {
-        long long v = 0;
-        const int64_t* co = M.ci.data() + (size_t)o * n;
-        for (int j = 0; j < n; ++j) v += co[j] * (long long)inc_x[j];
-        ov[o] = v;
-      }
-      model->points.add(inc_x.data(), ov);
-    }
-  }
-  return MOIP_OK;
+  return finish(inc_on_device);
 }
 
 #endif  // MOIP_HOST_DOUBLE

@@ -12,6 +12,7 @@
 #include "device.h"
 #include "model.h"
 #include "nodepool.h"
+#include "bbchain.h"
 
 namespace moip {
 
@@ -210,6 +211,22 @@ struct moip_ctx {
   std::atomic<int> dbg_where{0};
   std::atomic<long long> dbg_rounds{0}, dbg_open{0}, dbg_strip{-1};
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
+
+  // ---- chained rounds (bbchain.h): the tree of an IP advances on the device, the host looks in once per chunk of rounds
+  bool use_chain = true;       // MOIP_CHAIN=0: every round through the host (solve_ip's own loop)
+  bool chain_debug = false;    // MOIP_CHAIN_DEBUG=1: synchronise after every launch and say which one failed
+  int chain_q = 4096;          // pool rows per parity = widest tree level the device handles (MOIP_CHAIN_Q)
+  moip::DBuf<moip::BbCtl> d_ctl;
+  moip::HBuf<moip::BbCtl> h_ctl;
+  moip::HBuf<int> h_inc;
+  moip::DBuf<double> c_bound;
+  moip::DBuf<int> c_depth;
+  double chain_rounds_avg[MOIP_MAX_OBJ + 1] = {6, 6, 6, 6, 6};   // rounds per IP of each stage (sizes the first chunk)
+  long long chain_ips = 0, chain_fallbacks = 0, chain_chunks = 0, chain_idle_rounds = 0;
+  // returns MOIP_OK with `handled` set, or leaves `handled` false (level wider than chain_q ...): the caller's loop takes over,
+  // starting from the incumbent found so far (inc_val / inc_x updated)
+  int solve_ip_chained(int cost, const double* srhs, const long long* olo, const long long* ohi, bool& have_inc,
+                       long long& inc_val, std::vector<int>& inc_x, bool& handled);
 
   moip::DBuf<double> k1_scratch;   // streaming mode of the generic K1 kernel (models too large for shared memory)
   int attach_k1_scratch(moip::LpBatch& b);
