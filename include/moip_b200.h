@@ -190,6 +190,15 @@ typedef struct {
   int perm[MOIP_MAX_OBJ];    /* Thread::perm(i) (src/thread.h:37)  */
   int split;                 /* global `split`  (src/aira.cpp:38)  */
   double split_start, split_stop; /* Thread::split_start/stop (src/thread.h:25-26) */
+  /* Window on the objective of the innermost sweeps, perm[1] (no counterpart in the reference; 0 = off).  An EPP strip is a
+   * range of the LAST objective and starts with a whole (n_obj-1)-objective front of its own, so strips alone stop paying
+   * once that start-up outweighs a strip's share of the front.  A window cuts the other way: bounds of perm[1] start at
+   * win_start instead of "free", and a subproblem whose perm[1] bound lies beyond win_stop is taken as infeasible without
+   * being solved.  IPs are still solved WITHOUT a lower limit, so every point found is non-dominated for the whole model,
+   * and a point inside the window can only be skipped over by the answer of a solved IP, which the trackers then hold: the
+   * boxes (strip x window) of a level together enumerate the level's front.  Needs n_obj >= 3. */
+  int window;
+  double win_start, win_stop;
 } moip_worker;
 /* optimise<sense>() for one worker.  `all` / `infeasibles` are the two shared stores of
  * src/aira.cpp:539; found points are merged into `all` (:1877-1879). */
@@ -243,6 +252,11 @@ int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const double* sta
 typedef int (*moip_claim_fn)(void* user);
 int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, const double* start_stop, moip_claim_fn claim,
                                void* user, int* rows_out, int cap, int* n_rows);
+/* the same with a window on objective 1 per entry (moip_worker::window): windows[2t], windows[2t+1] = near / far edge of
+ * box t; boxes that share a range of the last objective split its start-up -- the (n_obj-1)-objective front every strip
+ * begins with -- between them.  n_obj >= 3 (ignored below). */
+int moip_pool_run_boxes_claim(moip_pool* p, int n_obj, int nboxes, const double* start_stop, const double* windows,
+                              moip_claim_fn claim, void* user, int* rows_out, int cap, int* n_rows);
 /* main() with --split -t num_threads (src/aira.cpp:269-276, :1945-1990): every level's strips run
  * concurrently on the pool; rows_out = sorted, de-duplicated front */
 int moip_pool_pareto_front(moip_pool* p, int num_threads, int split_normal, int* rows_out, int cap, int* n_rows);

@@ -60,7 +60,8 @@ class KernelTimes(C.Structure):
 
 class Worker(C.Structure):
     _fields_ = [("id", C.c_int), ("n_obj", C.c_int), ("perm", C.c_int * MAX_OBJ), ("split", C.c_int),
-                ("split_start", C.c_double), ("split_stop", C.c_double)]
+                ("split_start", C.c_double), ("split_stop", C.c_double),
+                ("window", C.c_int), ("win_start", C.c_double), ("win_stop", C.c_double)]
 
 
 SOLVE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_double),
@@ -124,6 +125,7 @@ _SIGS = {
     "moip_pool_get_limit": (_i, [_vp, _i, _i, _pd, _pi, _pi]),
     "moip_pool_run_strips": (_i, [_vp, _i, _i, _pd, _pi, _i, _pi]),
     "moip_pool_run_strips_claim": (_i, [_vp, _i, _i, _pd, CLAIM_FN, _vp, _pi, _i, _pi]),
+    "moip_pool_run_boxes_claim": (_i, [_vp, _i, _i, _pd, _pd, CLAIM_FN, _vp, _pi, _i, _pi]),
     "moip_pool_pareto_front": (_i, [_vp, _i, _i, _pi, _i, _pi]),
     "moip_coop_workers": (_i, [_i, _i, C.POINTER(Worker)]),
     "moip_coop_optimise_with": (_i, [_i, _i, _i, C.POINTER(Worker), SOLVE_FN, FIND_CB, INSERT_CB, C.POINTER(_vp),
@@ -397,15 +399,30 @@ class WorkerPool:
                                         C.byref(st)), "pool_get_limit")
         return st.value, ([int(v) for v in res] if st.value != MIP_INFEASIBLE else None)
 
-    def run_strips(self, n_obj, strips, claim=None, cap=1 << 20):
+    def run_strips(self, n_obj, strips, claim=None, cap=1 << 20, windows=None):
         """strips: list of (start, stop); returns the feasible result rows found (unsorted).  `claim`: optional
         callable returning the index of the next strip to solve (shared by the pools of several ranks); without it
-        the pool works through all the strips given."""
+        the pool works through all the strips given.  `windows`: one (near edge, far edge) pair per entry of `strips` --
+        the entries are then boxes, strip x window on objective 1 (moip_worker::window)."""
         k = self.problem.objcnt
         ss = np.ascontiguousarray(np.asarray(strips, dtype=np.float64).reshape(-1, 2))
         rows = np.zeros((cap, k), dtype=np.int32)
         n = C.c_int(0)
-        if claim is None:
+        if windows is not None:
+            ww = np.ascontiguousarray(np.asarray(windows, dtype=np.float64).reshape(-1, 2))
+            if len(ww) != len(ss):
+                raise MoipError("one window per strip entry")
+            if claim is None:
+                it = iter(range(len(ss)))
+                lock = __import__("threading").Lock()
+
+                def claim():
+                    with lock:
+                        return next(it, len(ss))
+            cb = CLAIM_FN(lambda _user: int(claim()))
+            _check(_lib.moip_pool_run_boxes_claim(self._h, int(n_obj), len(ss), _dp(ss), _dp(ww), cb, None, _ip(rows), cap,
+                                                  C.byref(n)), "pool_run_boxes_claim")
+        elif claim is None:
             _check(_lib.moip_pool_run_strips(self._h, int(n_obj), len(ss), _dp(ss), _ip(rows), cap, C.byref(n)), "pool_run_strips")
         else:
             cb = CLAIM_FN(lambda _user: int(claim()))
@@ -543,8 +560,10 @@ def split_strips(sense, biggest, smallest, num_threads, split_normal=False):
     return [(float(out[2 * t]), float(out[2 * t + 1])) for t in range(num_threads)]
 
 
-def make_worker(k, perm=None, n_obj=None, split=False, split_start=0.0, split_stop=0.0, wid=0):
+def make_worker(k, perm=None, n_obj=None, split=False, split_start=0.0, split_stop=0.0, wid=0, window=None):
     w = Worker()
+    if window is not None:
+        w.window, w.win_start, w.win_stop = 1, float(window[0]), float(window[1])
     w.id, w.n_obj, w.split = wid, int(n_obj or k), int(split)
     p = list(perm) if perm is not None else list(range(k))
     for i in range(MAX_OBJ):

@@ -218,12 +218,13 @@ class GpuBackend:
         st, res = self.pool.get_limit(obj, rhs)
         return res
 
-    def run_strips(self, n_obj, strips, claim, share=0):
+    def run_strips(self, n_obj, strips, claim, share=0, windows=None):
         """The strips of one EPP level: this rank's workers draw strip indices from `claim` (shared by all ranks),
         solve them concurrently and share `here`/`infeasibles` like the reference's threads.  share > 0: at most that
-        many strips in flight on this rank (its part of the level when there are fewer strips than workers in the job)."""
+        many strips in flight on this rank (its part of the level when there are fewer strips than workers in the job).
+        windows: one per entry of `strips` -- the entries are boxes (strip x window on objective 1)."""
         self.pool.set_max_workers(share)
-        return self.pool.run_strips(n_obj, strips, claim)
+        return self.pool.run_strips(n_obj, strips, claim, windows=windows)
 
     def exchange_endpoint(self):
         """what RecordExchange talks to: the pool's export_records / import_records"""
@@ -270,6 +271,38 @@ class GpuBackend:
         return self.stats().get("ip_solved", 0)
 
 
+def windows_for(n_obj, num_threads, world):
+    """How many windows on objective 1 the boxes of a level get.  MOIP_WINDOWS=<n> fixes it (1 = strips only); by default
+    strips only up to 32 strips (one GPU: the start-up of a strip is a small part of its work), beyond that one window per
+    8 strips, at most 16."""
+    if n_obj < 3:
+        return 1
+    env = os.environ.get("MOIP_WINDOWS")
+    if env:
+        return max(1, min(int(env), num_threads))
+    if num_threads <= 32:
+        return 1
+    nwin = 1
+    while nwin < 16 and num_threads // (nwin * 2) >= 12:
+        nwin *= 2
+    return nwin
+
+
+def window_edges(values, nwin, is_min):
+    """(near edge, far edge) of `nwin` windows on an objective whose values over the level below are `values` (sorted,
+    distinct): quantile cuts; the first window is open towards "free", the last has no far edge.  Bounds are upper limits
+    for MIN models and lower limits for MAX models, and a window ends one unit before the next one starts."""
+    big = 1e20
+    if nwin <= 1 or len(values) < 2 * nwin:
+        return [(big if is_min else -big, -big if is_min else big)]
+    cuts = sorted({values[len(values) * i // nwin] for i in range(1, nwin)})
+    if is_min:
+        near = [big] + [float(c) for c in reversed(cuts)]
+        return [(e, near[i + 1] + 1 if i + 1 < len(near) else -big) for i, e in enumerate(near)]
+    near = [-big] + [float(c) for c in cuts]
+    return [(e, near[i + 1] - 1 if i + 1 < len(near) else big) for i, e in enumerate(near)]
+
+
 def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list | None = None):
     """split_setup (src/aira.cpp:1945-1990) with each level's strips sharded over the ranks.  stats (a list) receives one
     dict per level: strips, exchange rounds, cache records sent / received by this rank."""
@@ -296,13 +329,29 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list 
             if biggest == smallest:
                 smallest = INT_MIN
         t_level = time.monotonic()
-        strips = be.split_strips(biggest, smallest, num_threads, split_normal)
+        # Boxes (moip_worker::window; no counterpart in the reference): with many more workers than a level has heavy strips,
+        # the level is cut both ways -- `nwin` windows on objective 1 (edges = quantiles of that objective over the level
+        # below, the first window open towards "free", the last without a far edge) times num_threads / nwin strips of the
+        # last objective.  A strip starts with an (n_obj-1)-objective front of its own; the boxes of one strip share that
+        # start-up between them instead of each paying for it.
+        nwin = windows_for(n_obj, num_threads, dist.world) if hasattr(be, "exchange_endpoint") or getattr(be, "boxes_ok", False) else 1
+        windows = None
+        if nwin > 1:
+            edges = window_edges(sorted({s[1] for s in lower}), nwin, is_min)
+            nwin = len(edges)
+        if nwin > 1:
+            base = be.split_strips(biggest, smallest, max(1, num_threads // nwin), split_normal)
+            strips = [st for st in base for _ in range(nwin)]
+            windows = [w for _ in base for w in edges]
+        else:
+            strips = be.split_strips(biggest, smallest, num_threads, split_normal)
         # Strip s belongs to rank s mod world: every rank gets an interleaved sample of the range -- light strips from its
         # ends and heavy ones from its middle (the points crowd there) -- so the ranks carry about the same load without
         # talking to each other; inside a rank, idle workers then cut busy strips in two (moip_pool_run_strips_claim).
         # MOIP_GLOBAL_STRIP_COUNTER=1: the ranks draw strips from one job-wide counter in the c10d store instead.
         if dist.world > 1 and not os.environ.get("MOIP_GLOBAL_STRIP_COUNTER"):
-            mine = iter([s_ for s_ in range(len(strips)) if s_ % dist.world == dist.rank] + [len(strips)] * 4096)
+            owner = (lambda b: (b // nwin + b % nwin) % dist.world) if nwin > 1 else (lambda b: b % dist.world)   # boxes: a Latin square of strips and windows
+            mine = iter([s_ for s_ in range(len(strips)) if owner(s_) == dist.rank] + [len(strips)] * 4096)
             lock = __import__("threading").Lock()
 
             def claim():
@@ -314,9 +363,9 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list 
             share = -(-len(strips) // dist.world) if dist.world > 1 else 0  # ceil: no rank claims more than its part at once
         endpoint = be.exchange_endpoint() if hasattr(be, "exchange_endpoint") else None
         with RecordExchange(dist, endpoint, k) as ex:
-            rows = be.run_strips(n_obj, strips, claim, share)
+            rows = be.run_strips(n_obj, strips, claim, share, windows) if windows is not None else be.run_strips(n_obj, strips, claim, share)
         if stats is not None:
-            stats.append({"n_obj": n_obj, "strips": len(strips), "exchange_rounds": ex.rounds, "records_sent": ex.sent,
+            stats.append({"n_obj": n_obj, "strips": len(strips), "windows": nwin, "exchange_rounds": ex.rounds, "records_sent": ex.sent,
                           "records_received": ex.received, "rows_here": len(rows),
                           "seconds": round(time.monotonic() - t_level, 3)})
         return dist.allgather_rows(rows, k)

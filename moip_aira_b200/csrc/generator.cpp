@@ -71,6 +71,13 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
   std::vector<int> res(k, 0), hi_seen(k, 0), lo_seen(k, 0);
   int status = 0, rc;
   const int last = perm[n_obj - 1];
+  // window on the objective of the innermost sweeps (moip_worker::window): its "free" bound is the window's near edge,
+  // and subproblems bounded beyond the far edge count as infeasible without being solved (or recorded)
+  const bool windowed = w.window != 0 && n_obj >= 3;
+  const int wobj = perm[1];
+  auto free_of = [&](int j) { return (windowed && j == wobj) ? w.win_start : free_rhs; };
+  auto beyond_window = [&]() { return windowed && (is_min ? rhs[wobj] < w.win_stop : rhs[wobj] > w.win_stop); };
+  rhs[wobj] = free_of(wobj);
   if (split) rhs[last] = split_start;                                       // :607
   if ((rc = be.solve(perm, n_obj, rhs.data(), res.data(), &status))) return rc;   // :614
   const bool root_infeasible = status == MOIP_MIP_INFEASIBLE;
@@ -98,7 +105,7 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
     int level = 1, depth = perm[level];
     bool walking = false, last_missed = false;
     int misses = 0;
-    for (int jp = 1; jp < k; ++jp) rhs[perm[jp]] = free_rhs;                // :733-756
+    for (int jp = 1; jp < k; ++jp) rhs[perm[jp]] = free_of(perm[jp]);       // :733-756
     if (split) rhs[last] = split_start;                                     // :757-759
     rhs[objective] = is_min ? (double)wrap32((int64_t)hi_seen[objective] - 1)
                             : (double)wrap32((int64_t)lo_seen[objective] + 1);   // :761-777
@@ -115,7 +122,8 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
                      k > 3 ? rhs[3] : 0.0, res[0], k > 1 ? res[1] : 0, k > 2 ? res[2] : 0, k > 3 ? res[3] : 0, hi_seen[0], k > 1 ? hi_seen[1] : 0,
                      k > 2 ? hi_seen[2] : 0, k > 3 ? hi_seen[3] : 0, lo_seen[0], k > 1 ? lo_seen[1] : 0, k > 2 ? lo_seen[2] : 0, k > 3 ? lo_seen[3] : 0);
       int hit = 0, infeasible = 0;
-      if ((rc = be.find(rhs.data(), &hit, &infeasible, res.data()))) return rc;   // :816-827
+      if (beyond_window()) { hit = 1; infeasible = 1; }
+      else if ((rc = be.find(rhs.data(), &hit, &infeasible, res.data()))) return rc;   // :816-827
       if (n_iter) ++*n_iter;
       if (hit) { if (n_hit) ++*n_hit; }
       else {
@@ -134,14 +142,14 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
       if (infeasible) { ++misses; last_missed = true; } else { misses = 0; last_missed = false; }
       // next bound vector (:1575-1832)
       if (infeasible && misses == active - 1) {
-        for (int j = 0; j < k; ++j) rhs[j] = free_rhs;                      // :1586-1599
+        for (int j = 0; j < k; ++j) rhs[j] = free_of(j);                    // :1586-1599
         if (split) rhs[n_obj - 1] = split_start;                            // :1649-1651
         tighten(objective);                                                 // :1655-1673
         publish_progress(active);
         if (!split && active == n_obj - 1) be.outer_bound_moved(objective, rhs[objective]);
         level = 1; depth = perm[level]; walking = false;
       } else if (last_missed && misses != active) {
-        rhs[depth] = free_rhs;                                              // :1722-1728
+        rhs[depth] = free_of(depth);                                        // :1722-1728
         depth = perm[++level];                                              // :1730-1731
         tighten(depth);                                                     // :1758-1760 / :1778-1780
         walking = true;
@@ -735,8 +743,24 @@ extern "C" int moip_pool_run_strips(moip_pool* p, int n_obj, int nstrips, const 
 // Same, but every worker asks `claim` for the index of its next strip (values >= nstrips end the worker): lets
 // several pools -- one per GPU / rank -- draw from one global counter, so that no rank idles while another still
 // has strips queued.  claim == nullptr: local counter.
+static int run_boxes(moip_pool* p, int n_obj, int nstrips, const double* start_stop, const double* windows, moip_claim_fn claim,
+                     void* user, int* rows_out, int cap, int* n_rows);
+
 extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, const double* start_stop, moip_claim_fn claim,
                                           void* user, int* rows_out, int cap, int* n_rows) {
+  return run_boxes(p, n_obj, nstrips, start_stop, nullptr, claim, user, rows_out, cap, n_rows);
+}
+
+// Boxes: strip t additionally carries a window (windows[2t], windows[2t+1]) on objective 1 (moip_worker::window); several
+// boxes may share one range of the last objective.  A strip cut off a busy box by an idle worker inherits its window.
+extern "C" int moip_pool_run_boxes_claim(moip_pool* p, int n_obj, int nboxes, const double* start_stop, const double* windows,
+                                         moip_claim_fn claim, void* user, int* rows_out, int cap, int* n_rows) {
+  if (nboxes > 0 && !windows) return MOIP_ERR_ARG;
+  return run_boxes(p, n_obj, nboxes, start_stop, windows, claim, user, rows_out, cap, n_rows);
+}
+
+static int run_boxes(moip_pool* p, int n_obj, int nstrips, const double* start_stop, const double* windows, moip_claim_fn claim,
+                     void* user, int* rows_out, int cap, int* n_rows) {
   if (!p || p->ctx.empty() || nstrips < 0 || (nstrips > 0 && !start_stop) || !n_rows) return MOIP_ERR_ARG;
   const int k = p->ctx[0]->dm.k;
   if (n_obj < 1 || n_obj > k) return MOIP_ERR_ARG;
@@ -753,6 +777,7 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
   std::vector<StripDyn> dyn((size_t)std::max(1, max_strips));
   std::vector<double> sstart((size_t)std::max(1, max_strips), 0.0);
   std::vector<int> cut_from((size_t)std::max(1, max_strips), -1);
+  std::vector<double> swin(windows ? 2 * (size_t)std::max(1, max_strips) : 0, 0.0);   // window of every (claimed or cut) strip
   std::atomic<int> next(0), failed(0), n_dyn(nstrips), n_claiming(W), n_stolen(0);
   std::mutex steal_mu;
   // a cut must leave both halves worth a strip's start-up cost (a lower-dimensional front of its own): at least
@@ -794,6 +819,7 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
     const double mid = is_min ? pos - std::floor(widest / 2) : pos + std::floor(widest / 2);
     sstart[nd] = mid;
     cut_from[nd] = victim;
+    if (windows) { swin[2 * (size_t)nd] = swin[2 * (size_t)victim]; swin[2 * (size_t)nd + 1] = swin[2 * (size_t)victim + 1]; }
     dyn[nd].stop.store(stop); dyn[nd].pos.store(mid); dyn[nd].state.store(1, std::memory_order_release);
     dyn[victim].stop.store(mid, std::memory_order_release);
     n_dyn.store(nd + 1);
@@ -834,6 +860,7 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
         if (t < 0 || t >= nstrips) { claims_left = false; t = -1; n_claiming.fetch_sub(1); }
         else {
           sstart[t] = start_stop[2 * t];
+          if (windows) { swin[2 * (size_t)t] = windows[2 * t]; swin[2 * (size_t)t + 1] = windows[2 * t + 1]; }
           dyn[t].stop.store(start_stop[2 * t + 1]); dyn[t].pos.store(start_stop[2 * t]);
           dyn[t].state.store(1, std::memory_order_release);
         }
@@ -848,6 +875,7 @@ extern "C" int moip_pool_run_strips_claim(moip_pool* p, int n_obj, int nstrips, 
       w.id = t; w.n_obj = n_obj; w.split = 1;
       for (int i = 0; i < k; ++i) w.perm[i] = i;                            // thread.cpp:124-133
       w.split_start = sstart[t]; w.split_stop = dyn[t].stop.load();
+      if (windows) { w.window = 1; w.win_start = swin[2 * (size_t)t]; w.win_stop = swin[2 * (size_t)t + 1]; }
       c->dbg_strip.store(t, std::memory_order_relaxed);
       if (timeline) { slog[t].worker = wi; slog[t].t0 = since0(); slog[t].start = sstart[t]; slog[t].stop0 = w.split_stop; slog[t].ips = c->stats.ip_solved; slog[t].from = cut_from[t]; }
       rc = optimise_strip(c, &w, here, infeasibles, steal && shared ? &dyn[t] : nullptr);

@@ -416,3 +416,67 @@ def test_pool_record_exchange_is_a_noop_between_runs(lib, examples):
     assert lib._lib.moip_pool_export_records(None, 0, None, None, None, C.byref(n)) == 1
     assert lib._lib.moip_pool_import_records(None, 0, None, None, None) == 1
     assert lib._lib.moip_pool_set_max_workers(None, 1) == 1
+
+
+def _windows(lo, hi, count, is_min):
+    """`count` windows on an objective whose front values lie in [lo, hi]: (near edge, far edge) pairs; the first is open
+    towards "free", the last has no far edge.  Bounds are upper limits for MIN models, lower limits for MAX models."""
+    big = 1e20
+    if count <= 1 or hi <= lo:
+        return [(big if is_min else -big, -big if is_min else big)]
+    cuts = sorted({lo + (hi - lo) * i // count for i in range(1, count)})
+    out = []
+    if is_min:
+        edges = [big] + [float(c) for c in reversed(cuts)]           # near edges, from the top
+        for i, e in enumerate(edges):
+            far = edges[i + 1] + 1 if i + 1 < len(edges) else -big   # the next window starts at cut, this one ends at cut + 1
+            out.append((e, far))
+    else:
+        edges = [-big] + [float(c) for c in cuts]
+        for i, e in enumerate(edges):
+            far = edges[i + 1] - 1 if i + 1 < len(edges) else big
+            out.append((e, far))
+    return out
+
+
+@pytest.mark.parametrize("kind,k,n,seed", [("kp", 3, 11, 21), ("kp", 4, 10, 22), ("kp", 3, 12, 23), ("ap", 3, 4, 24),
+                                           ("ap", 4, 3, 25), ("kp", 4, 9, 26), ("ap", 3, 4, 27), ("kp", 3, 10, 28)])
+@pytest.mark.parametrize("strips,wins,shared", [(1, 2, True), (2, 3, True), (3, 4, False), (4, 2, True), (2, 5, False)])
+def test_generator_boxes_enumerate_the_front(lib, tmp_path, kind, k, n, seed, strips, wins, shared):
+    """EPP strips (ranges of the last objective) crossed with windows on the objective of the innermost sweeps
+    (moip_worker::window): the boxes of the top level together enumerate exactly the brute-force front, with one pair of
+    stores shared by all boxes (what a pool does) or a pair per box."""
+    from moip_aira_b200 import instances
+    path = str(tmp_path / f"{kind}{k}_{n}_{seed}.lp")
+    (instances.write_ap if kind == "ap" else instances.write_kp)(path, n, k, seed)
+    m = read_model(path)
+    fs = ao.FeasibleSet(m)
+    is_min = m.sense == "MIN"
+    want = _nondominated(fs.P, is_min)
+    last = [p[k - 1] for p in want]
+    ss = lib.split_strips(0 if is_min else 1, max(last), min(last), strips, False)
+    w1 = [p[1] for p in want]
+    found = set()
+    stores = (ao.Solutions(k), ao.Solutions(k))
+    solved = 0
+    for t in range(strips):
+        for win in _windows(min(w1), max(w1), wins, is_min):
+            s, inf = stores if shared else (ao.Solutions(k), ao.Solutions(k))
+
+            def find(ip):
+                _, r = inf.find(ip, m.sense)
+                if r is None:
+                    _, r = s.find(ip, m.sense)
+                return None if r is None else (r.infeasible, r.result)
+
+            def insert(ip, res, infeasible):
+                (inf if infeasible else s).insert(ip, res, infeasible)
+
+            def solve(perm, n_obj, rhs):
+                nonlocal solved
+                solved += 1
+                return fs.lex_solve(perm, n_obj, rhs)
+            w = lib.make_worker(k, split=True, split_start=ss[t][0], split_stop=ss[t][1], wid=t, window=win)
+            lib.optimise_with(k, 0 if is_min else 1, w, solve, find, insert)
+            found |= {tuple(r.result) for r in s.store if not r.infeasible}
+    assert sorted(found, reverse=True) == want

@@ -26,7 +26,12 @@ for spec in sys.argv[1:]:
     for k_ in envs:
         os.environ.pop(k_, None)
     if rank == 0:
-        pr = [{a: p.get(a) for a in ("rank", "busy_s", "ips", "strips_cut_by_idle_workers", "solver_s", "kernel_ms")} | {"level_s": [l["seconds"] for l in p["levels"]], "rec_rx": [l["records_received"] for l in p["levels"]]} for p in r["per_rank"]]
-        print(f"{spec}: {r['seconds']:.3f}s ok={r['matches_golden']} ips={r['ips']} node_lps={r['node_lps']} strips={r['strips']} per_rank={json.dumps(pr)}", flush=True)
+        pr = r["per_rank"]
+        ips = [p["ips"] for p in pr]
+        print(f"{spec}: {r['seconds']:.3f}s ok={r['matches_golden']} ips={r['ips']} node_lps={r['node_lps']} strips={r['strips']} "
+              f"windows={[l.get('windows') for l in pr[0]['levels']]} level_s={[l['seconds'] for l in pr[0]['levels']]} "
+              f"ips/rank={min(ips)}..{max(ips)} cuts={sum(p['strips_cut_by_idle_workers'] for p in pr)} "
+              f"solver_s/rank={min(p['solver_s'] for p in pr)}..{max(p['solver_s'] for p in pr)} "
+              f"rec_rx={[l['records_received'] for l in pr[0]['levels']]}", flush=True)
 if world > 1:
     dist.destroy_process_group()
