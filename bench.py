@@ -205,8 +205,8 @@ def main():
     ap.add_argument("--front-instances", default="ap3_30_1,kp4_40_1",
                     help="synthetic instances (tests/golden) whose Pareto fronts are timed with the EPP strips sharded over the ranks")
     ap.add_argument("--front-strips-per-gpu", type=int, default=0,
-                    help="EPP strips per GPU (0 = one per solver context for 3-objective instances, a quarter of that for 4 "
-                         "objectives, where every strip starts with a 3-objective front of its own; idle workers cut busy strips)")
+                    help="boxes per GPU (0 = four per solver context): EPP strips of the last objective x windows on objective 1 "
+                         "(aira.windows_for); idle workers cut busy boxes")
     ap.add_argument("--front-budget-s", type=float, default=600.0,
                     help="wall-clock budget of the time-to-front section: when it runs out the line is printed with what is there")
     ap.add_argument("--syn-instances", default="ap3_30_1,kp4_40_1",
@@ -413,7 +413,7 @@ def main():
         ttf["examples --split -t 8"] = {stem: example_epp(stem, 8, local, tmp) for stem in ("4AP05", "4KP10")}
         for name in [x for x in args.front_instances.split(",") if x]:
             from moip_aira_b200 import aira
-            per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else (aira.default_workers() if parse_instance(name)[1] <= 3 else 4)
+            per_gpu = args.front_strips_per_gpu if args.front_strips_per_gpu > 0 else 4 * aira.default_workers()
             ttf[f"{name} --split -t {per_gpu * world}"] = synthetic_front(name, per_gpu * world, local, tmp)
         for name in [x for x in args.syn_instances.split(",") if x]:
             ttf[f"{name} synergistic"] = synergistic(name, local, tmp)
@@ -482,6 +482,7 @@ def _front_job(path, golden_rows, device, run):
     per_rank = _gather({"rank": d.rank, "busy_s": round(mine, 3), "ips": int(be.ip_count() - ips0),
                         "node_lps": int(st.get("node_lps", 0)), "bb_nodes": int(st.get("bb_nodes", 0)),
                         "strips_cut_by_idle_workers": be.pool.strips_stolen() if be._pool is not None else 0,
+                        "boxes_postponed": be.pool.boxes_postponed() if be._pool is not None else 0,
                         "solver_s": round(float(st.get("solver_seconds", 0.0)), 2),
                         "kernel_ms": ({a: round(v) for a, v in be.pool.kernel_times().items()} if os.environ.get("MOIP_KERNEL_TIMING") and be._pool is not None else None),
                         **(extra or {})})

@@ -31,6 +31,7 @@ extern "C" {
 #define MOIP_ERR_CUDA 3
 #define MOIP_ERR_UNSUPPORTED 4
 #define MOIP_ERR_LIMIT 5
+#define MOIP_ERR_BUDGET 6   /* an IP was given up at its node budget (moip_ctx_set_ip_node_budget); nothing was recorded */
 /* MIP statuses: the values the reference compares against after CPXgetstat
  * (src/aira.cpp:489-492, :644, :840).  Kept numerically equal to CPLEX's so that
  * `solnstat == CPXMIP_INFEASIBLE` keeps working when solve() forwards our status. */
@@ -176,6 +177,10 @@ int moip_ctx_set_kernel_timing(moip_ctx* c, int on);
  * a blocking event (for more workers than cores).  MOIP_SYNC=spin|block overrides; pools choose by core count (auto). */
 int moip_ctx_set_sync_mode(moip_ctx* c, int blocking);
 int moip_ctx_kernel_times(const moip_ctx* c, moip_kernel_times* out);
+/* Node budget per IP (0 = none, the default): moip_lex_solve / moip_get_limit return MOIP_ERR_BUDGET once the B&B tree of one
+ * of their IPs has processed more nodes than this.  The box scheduler (moip_pool_run_boxes_claim) uses it to postpone a box
+ * whose cold first subproblem explodes until the records of its neighbours answer it. */
+int moip_ctx_set_ip_node_budget(moip_ctx* c, long long nodes);
 
 /* ---- subproblem generator re-hosted on the boundary above (src/aira.cpp:538-1884 without the
  * inter-thread bound cells, and the EPP driver src/aira.cpp:1886-1990) -------------------------- */
@@ -242,6 +247,8 @@ int moip_pool_exchange_counts(const moip_pool* p, int64_t* exported, int64_t* im
  * worker that finds none left take over the far half of the widest range a busy strip has not reached yet: a strip is
  * only a range of the last objective (src/aira.cpp:1895-1916), so the front is the same (MOIP_NO_STEAL=1 disables). */
 int64_t moip_pool_strips_stolen(const moip_pool* p);
+/* boxes put back because their first subproblem ran into its node budget (moip_pool_run_boxes_claim), since pool creation */
+int64_t moip_pool_boxes_postponed(const moip_pool* p);
 int moip_pool_get_limit(moip_pool* p, int obj, int sense, const double* rhs, int* result, int* mip_status);
 /* split_optimise (src/aira.cpp:1886-1943) for nstrips explicit (start, stop) pairs, dealt dynamically to
  * the workers; rows_out receives the feasible result vectors (k ints per row, unsorted) */

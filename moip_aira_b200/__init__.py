@@ -105,6 +105,7 @@ _SIGS = {
     "moip_ctx_reset_stats": (_i, [_vp]),
     "moip_ctx_set_kernel_timing": (_i, [_vp, _i]),
     "moip_ctx_set_sync_mode": (_i, [_vp, _i]),
+    "moip_ctx_set_ip_node_budget": (_i, [_vp, C.c_longlong]),
     "moip_ctx_kernel_times": (_i, [_vp, C.POINTER(KernelTimes)]),
     "moip_pool_set_kernel_timing": (_i, [_vp, _i]),
     "moip_pool_kernel_times": (_i, [_vp, C.POINTER(KernelTimes)]),
@@ -113,6 +114,7 @@ _SIGS = {
     "moip_pool_import_records": (_i, [_vp, _i, _pd, _pi, _pi]),
     "moip_pool_exchange_counts": (_i, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "moip_pool_strips_stolen": (C.c_int64, [_vp]),
+    "moip_pool_boxes_postponed": (C.c_int64, [_vp]),
     "moip_optimise": (_i, [_vp, C.POINTER(Worker), _vp, _vp]),
     "moip_optimise_with": (_i, [_i, _i, C.POINTER(Worker), SOLVE_FN, FIND_CB, INSERT_CB, _vp,
                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -478,6 +480,9 @@ class WorkerPool:
 
     def strips_stolen(self):
         return int(_lib.moip_pool_strips_stolen(self._h))
+
+    def boxes_postponed(self):
+        return int(_lib.moip_pool_boxes_postponed(self._h))
 
     def exchange_counts(self):
         a, b = C.c_int64(0), C.c_int64(0)

@@ -272,18 +272,15 @@ class GpuBackend:
 
 
 def windows_for(n_obj, num_threads, world):
-    """How many windows on objective 1 the boxes of a level get.  MOIP_WINDOWS=<n> fixes it (1 = strips only); by default
-    strips only up to 32 strips (one GPU: the start-up of a strip is a small part of its work), beyond that one window per
-    8 strips, at most 16."""
+    """How many windows on objective 1 the boxes of a level get: the largest power of two (at most 16) that leaves at least
+    8 strips of the last objective.  MOIP_WINDOWS=<n> fixes it (1 = strips only, the reference's cut)."""
     if n_obj < 3:
         return 1
     env = os.environ.get("MOIP_WINDOWS")
     if env:
         return max(1, min(int(env), num_threads))
-    if num_threads <= 32:
-        return 1
     nwin = 1
-    while nwin < 16 and num_threads // (nwin * 2) >= 12:
+    while nwin < 16 and num_threads // (nwin * 2) >= 8:
         nwin *= 2
     return nwin
 
@@ -329,22 +326,33 @@ def epp_front(be, dist: Dist, num_threads: int, split_normal: bool, stats: list 
             if biggest == smallest:
                 smallest = INT_MIN
         t_level = time.monotonic()
+        # The levels below the top one only supply the range of the next objective and are small fronts: with the top level's
+        # strip count (one per worker of the whole job) most of their strips would hold nothing but their start-up.
+        # MOIP_LOWER_STRIPS=<n> overrides (0 = as many as the top level, the reference's behaviour).
+        if n_obj < k and (hasattr(be, "exchange_endpoint") or getattr(be, "boxes_ok", False)):
+            cap_lower = int(os.environ.get("MOIP_LOWER_STRIPS", str(max(16, 4 * dist.world))))
+            if cap_lower > 0:
+                num_threads_here = min(num_threads, cap_lower)
+            else:
+                num_threads_here = num_threads
+        else:
+            num_threads_here = num_threads
         # Boxes (moip_worker::window; no counterpart in the reference): with many more workers than a level has heavy strips,
         # the level is cut both ways -- `nwin` windows on objective 1 (edges = quantiles of that objective over the level
-        # below, the first window open towards "free", the last without a far edge) times num_threads / nwin strips of the
+        # below, the first window open towards "free", the last without a far edge) times num_threads_here / nwin strips of the
         # last objective.  A strip starts with an (n_obj-1)-objective front of its own; the boxes of one strip share that
         # start-up between them instead of each paying for it.
-        nwin = windows_for(n_obj, num_threads, dist.world) if hasattr(be, "exchange_endpoint") or getattr(be, "boxes_ok", False) else 1
+        nwin = windows_for(n_obj, num_threads_here, dist.world) if hasattr(be, "exchange_endpoint") or getattr(be, "boxes_ok", False) else 1
         windows = None
         if nwin > 1:
             edges = window_edges(sorted({s[1] for s in lower}), nwin, is_min)
             nwin = len(edges)
         if nwin > 1:
-            base = be.split_strips(biggest, smallest, max(1, num_threads // nwin), split_normal)
+            base = be.split_strips(biggest, smallest, max(1, num_threads_here // nwin), split_normal)
             strips = [st for st in base for _ in range(nwin)]
             windows = [w for _ in base for w in edges]
         else:
-            strips = be.split_strips(biggest, smallest, num_threads, split_normal)
+            strips = be.split_strips(biggest, smallest, num_threads_here, split_normal)
         # Strip s belongs to rank s mod world: every rank gets an interleaved sample of the range -- light strips from its
         # ends and heavy ones from its middle (the points crowd there) -- so the ranks carry about the same load without
         # talking to each other; inside a rank, idle workers then cut busy strips in two (moip_pool_run_strips_claim).

@@ -37,6 +37,8 @@ struct GenBackend {
   // The top-level bound of the LAST stage (objective perm[n_obj-1]) has moved to new_rhs: every non-dominated point
   // beyond it has been recorded.  Only the cooperative workers (CoopBackend below) listen.
   virtual void outer_bound_moved(int /*objective*/, double /*new_rhs*/) {}
+  // node budget of the IPs behind the next solve() calls (0 = none): solve() then may return MOIP_ERR_BUDGET
+  virtual void set_budget(long long /*nodes*/) {}
 };
 
 // A strip whose END can move while it is being solved: an idle worker of the pool takes over the far half of the range
@@ -59,7 +61,10 @@ inline int wrap32(int64_t v) { return (int32_t)(uint32_t)(uint64_t)v; }
 
 }  // namespace
 
-int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* n_iter, int64_t* n_hit, StripDyn* dyn = nullptr) {
+// first_budget > 0 (boxes only): the cold first subproblem of a box is looked up in the stores first and, on a miss, solved
+// under this node budget; MOIP_ERR_BUDGET then means "nothing done, try this box again later".
+int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* n_iter, int64_t* n_hit, StripDyn* dyn = nullptr,
+               long long first_budget = 0) {
   const bool is_min = sense == MOIP_SENSE_MIN;
   const double free_rhs = is_min ? kInf : -kInf;
   const int* perm = w.perm;
@@ -79,9 +84,20 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
   auto beyond_window = [&]() { return windowed && (is_min ? rhs[wobj] < w.win_stop : rhs[wobj] > w.win_stop); };
   rhs[wobj] = free_of(wobj);
   if (split) rhs[last] = split_start;                                       // :607
-  if ((rc = be.solve(perm, n_obj, rhs.data(), res.data(), &status))) return rc;   // :614
-  const bool root_infeasible = status == MOIP_MIP_INFEASIBLE;
-  if ((rc = be.insert(rhs.data(), res.data(), root_infeasible ? 1 : 0))) return rc;   // :644-651
+  bool root_known = false, root_infeasible = false;
+  if (windowed) {       // a box starts inside the front: its first subproblem may already be answered by a neighbour's records
+    int hit = 0, inf0 = 0;
+    if ((rc = be.find(rhs.data(), &hit, &inf0, res.data()))) return rc;
+    if (hit) { root_known = true; root_infeasible = inf0 != 0; }
+  }
+  if (!root_known) {
+    if (windowed && first_budget > 0) be.set_budget(first_budget);
+    rc = be.solve(perm, n_obj, rhs.data(), res.data(), &status);              // :614
+    if (windowed && first_budget > 0) be.set_budget(0);
+    if (rc) return rc;
+    root_infeasible = status == MOIP_MIP_INFEASIBLE;
+    if ((rc = be.insert(rhs.data(), res.data(), root_infeasible ? 1 : 0))) return rc;   // :644-651
+  }
   if (root_infeasible) return MOIP_OK;   // nothing lies inside these bounds (reference: trackers undefined)
   if (split) stop_adj = is_min ? -1.0 : 1.0;                                // :653-657
   hi_seen = res; lo_seen = res;                                             // :693-697
@@ -142,6 +158,11 @@ int run_worker(GenBackend& be, int k, int sense, const moip_worker& w, int64_t* 
       if (infeasible) { ++misses; last_missed = true; } else { misses = 0; last_missed = false; }
       // next bound vector (:1575-1832)
       if (infeasible && misses == active - 1) {
+        // Boxes: a sweep that saw no point at all leaves the tracker of the stage's objective at its reset value, and the
+        // reference's tighten() would wrap the bound to INT_MAX / INT_MIN -- "free" -- and walk the whole front beyond the
+        // strip again (harmless duplicates there).  Inside a window that walk starts with the window's tightest subproblem
+        // under no other bound, the one case plain B&B explodes on; nothing is left in the box, so the stage ends here.
+        if (windowed && (is_min ? hi_seen[objective] == INT_MIN : lo_seen[objective] == INT_MAX)) break;
         for (int j = 0; j < k; ++j) rhs[j] = free_of(j);                    // :1586-1599
         if (split) rhs[n_obj - 1] = split_start;                            // :1649-1651
         tighten(objective);                                                 // :1655-1673
@@ -176,6 +197,7 @@ struct GpuBackend : GenBackend {
   int solve(const int* perm, int n_obj, const double* rhs, int* result, int* status) override {
     return c->lex_solve(perm, n_obj, rhs, result, status);
   }
+  void set_budget(long long nodes) override { c->ip_node_budget = nodes; }
   int find(const double* rhs, int* hit, int* infeasible, int* result) override {
     int idx = -1, which = -1;
     CacheRecord r{};
@@ -215,13 +237,15 @@ struct CallbackBackend : GenBackend {
 
 using namespace moip;
 
-static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles, moip::StripDyn* dyn);
+static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles, moip::StripDyn* dyn,
+                          long long first_budget = 0);
 
 extern "C" int moip_optimise(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles) {
   return optimise_strip(c, w, all, infeasibles, nullptr);
 }
 
-static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles, moip::StripDyn* dyn) {
+static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, moip_cache* infeasibles, moip::StripDyn* dyn,
+                          long long first_budget) {
   if (!c || !w || !all || !infeasibles || w->n_obj < 1 || w->n_obj > c->dm.k) return MOIP_ERR_ARG;
   const int sense = c->model->M.sense;
   moip_cache* local = nullptr;                       // `Solutions s(p.objcnt)` (src/aira.cpp:587)
@@ -229,7 +253,7 @@ static int optimise_strip(moip_ctx* c, const moip_worker* w, moip_cache* all, mo
   if (rc) return rc;
   GpuBackend be;
   be.c = c; be.infeasibles = infeasibles; be.sols = w->split ? all : local; be.sense = sense;
-  rc = run_worker(be, c->dm.k, sense, *w, nullptr, nullptr, dyn);
+  rc = run_worker(be, c->dm.k, sense, *w, nullptr, nullptr, dyn, first_budget);
   if (!rc && moip_cache_size(local) > 0) {           // (EPP strips write straight into `all`: nothing to splice)
     moip_cache_sort_unique(local, nullptr, 0);       // :1877
     rc = moip_cache_merge(all, local);               // :1879
@@ -563,6 +587,7 @@ struct moip_pool {
   std::vector<moip_ctx*> ctx;
   std::vector<cudaStream_t> streams;
   int max_workers = 0;                       // 0 = every context may draw strips (moip_pool_set_max_workers)
+  long long deferrals = 0;                   // boxes postponed at their node budget (run_boxes)
   // the shared stores of the EPP level being solved (nullptr between runs): what the knowledge exchange between the
   // pools of several ranks reads and feeds (moip_pool_export_records / moip_pool_import_records)
   std::mutex run_mu;
@@ -692,6 +717,7 @@ extern "C" int moip_pool_import_records(moip_pool* p, int n, const double* ip, c
 }
 
 extern "C" int64_t moip_pool_strips_stolen(const moip_pool* p) { return p ? p->stolen : -1; }
+extern "C" int64_t moip_pool_boxes_postponed(const moip_pool* p) { return p ? p->deferrals : -1; }
 
 extern "C" int moip_pool_exchange_counts(const moip_pool* p, int64_t* exported, int64_t* imported) {
   if (!p) return MOIP_ERR_ARG;
@@ -837,6 +863,15 @@ static int run_boxes(moip_pool* p, int n_obj, int nstrips, const double* start_s
     std::lock_guard<std::mutex> rl(p->run_mu);
     p->run_here = sh_here; p->run_inf = sh_inf; p->exp_cursor[0] = p->exp_cursor[1] = 0;
   }
+  // Boxes whose cold first subproblem ran into its node budget wait here until nothing else is left to claim; by then the
+  // records of their neighbours usually answer that subproblem (the box that contains the edge of the feasible region
+  // proves "nothing beyond" the cheap way, just past its last point).  Budget: 20 000 nodes, x 8 per further attempt, none
+  // from the fourth attempt on (MOIP_BOX_BUDGET; 0 = never postpone).
+  const long long box_budget0 = windows ? (std::getenv("MOIP_BOX_BUDGET") ? std::atoll(std::getenv("MOIP_BOX_BUDGET")) : 20000) : 0;
+  std::vector<std::pair<int, int>> deferred;            // (box, attempts so far)
+  std::vector<int> attempts((size_t)std::max(1, max_strips), 0);
+  std::mutex deferred_mu;
+  std::atomic<int> n_deferred(0), n_deferrals(0);
   std::vector<std::vector<int>> found(W);
   // MOIP_STRIP_TIMELINE=1: one line per strip at the end of the level (who solved it, when, how many IPs, cut off whom)
   struct StripLog { int worker = -1, from = -1; double t0 = 0, t1 = 0, start = 0, stop0 = 0, stop1 = 0; long long ips = 0; };
@@ -865,10 +900,20 @@ static int run_boxes(moip_pool* p, int n_obj, int nstrips, const double* start_s
           dyn[t].state.store(1, std::memory_order_release);
         }
       }
+      if (t < 0 && n_deferred.load() > 0) {               // a postponed box: its turn comes when the claims have run out
+        std::lock_guard<std::mutex> lk(deferred_mu);
+        if (!deferred.empty()) {
+          t = deferred.front().first;
+          deferred.erase(deferred.begin());
+          n_deferred.fetch_sub(1);
+          dyn[t].pos.store(start_stop[2 * t]);             // (its end stays where a cut may have moved it meanwhile)
+          dyn[t].state.store(1, std::memory_order_release);
+        }
+      }
       if (t < 0) {
         if (!steal || !shared || failed.load()) break;
         t = try_steal();
-        if (t == -2 && n_claiming.load() == 0) break;                       // nothing running, nothing left to claim: the level is done
+        if (t == -2 && n_claiming.load() == 0 && n_deferred.load() == 0) break;   // nothing running, nothing left to claim: the level is done
         if (t < 0) { std::this_thread::sleep_for(std::chrono::microseconds(200)); continue; }
       }
       moip_worker w{};
@@ -878,7 +923,18 @@ static int run_boxes(moip_pool* p, int n_obj, int nstrips, const double* start_s
       if (windows) { w.window = 1; w.win_start = swin[2 * (size_t)t]; w.win_stop = swin[2 * (size_t)t + 1]; }
       c->dbg_strip.store(t, std::memory_order_relaxed);
       if (timeline) { slog[t].worker = wi; slog[t].t0 = since0(); slog[t].start = sstart[t]; slog[t].stop0 = w.split_stop; slog[t].ips = c->stats.ip_solved; slog[t].from = cut_from[t]; }
-      rc = optimise_strip(c, &w, here, infeasibles, steal && shared ? &dyn[t] : nullptr);
+      const long long budget = (windows && t < nstrips && attempts[t] < 3) ? box_budget0 << (3 * attempts[t]) : 0;
+      rc = optimise_strip(c, &w, here, infeasibles, steal && shared ? &dyn[t] : nullptr, budget);
+      if (rc == MOIP_ERR_BUDGET) {                        // nothing recorded: put the box back
+        rc = MOIP_OK;
+        attempts[t] += 1;
+        n_deferrals.fetch_add(1);
+        dyn[t].state.store(0, std::memory_order_release);
+        { std::lock_guard<std::mutex> lk(deferred_mu); deferred.emplace_back(t, attempts[t]); n_deferred.fetch_add(1); }
+        c->dbg_strip.store(-1, std::memory_order_relaxed);
+        if (!claims_left) std::this_thread::sleep_for(std::chrono::milliseconds(2));   // only postponed boxes are left: give the records time to arrive
+        continue;
+      }
       if (timeline) { slog[t].t1 = since0(); slog[t].stop1 = dyn[t].stop.load(); slog[t].ips = c->stats.ip_solved - slog[t].ips; }
       c->dbg_strip.store(-1, std::memory_order_relaxed);
       dyn[t].state.store(2, std::memory_order_release);
@@ -933,6 +989,7 @@ static int run_boxes(moip_pool* p, int n_obj, int nstrips, const double* start_s
       p->run_here = nullptr; p->run_inf = nullptr;
     }
     p->stolen += n_stolen.load();
+    p->deferrals += n_deferrals.load();
     if (!failed.load())      // (records imported from other ranks are reported by the rank that found them)
       for (auto& r : sh_here->host) if (!r.infeasible && !r.pad[0]) found[0].insert(found[0].end(), r.result, r.result + k);
     moip_cache_destroy(sh_here);

@@ -182,6 +182,12 @@ extern "C" int moip_ctx_set_sync_mode(moip_ctx* c, int blocking) {
   return MOIP_OK;
 }
 
+extern "C" int moip_ctx_set_ip_node_budget(moip_ctx* c, long long nodes) {
+  if (!c) return MOIP_ERR_ARG;
+  c->ip_node_budget = nodes > 0 ? nodes : 0;
+  return MOIP_OK;
+}
+
 extern "C" int moip_ctx_set_kernel_timing(moip_ctx* c, int on) {
   if (!c) return MOIP_ERR_ARG;
   MOIP_CUDA(cudaSetDevice(c->device));
@@ -709,6 +715,7 @@ int moip_ctx::solve_ip_chained(int cost, const double* srhs, const long long* ol
   const int stage = cur_stage;
   int chunk = std::min(16, std::max(2, (int)std::ceil(chain_rounds_avg[stage] + 0.5)));
   int r = 0;
+  bool over_budget = false;
   const BbCtl* H = h_ctl.p;
   for (;;) {
     for (int c = 0; c < chunk; ++c, ++r) {
@@ -739,6 +746,7 @@ int moip_ctx::solve_ip_chained(int cost, const double* srhs, const long long* ol
     if (wait_stream()) return MOIP_ERR_CUDA;
     dbg_rounds.store(r, std::memory_order_relaxed); dbg_open.store(H->count[r & 1], std::memory_order_relaxed);
     if (H->overflow || H->count[r & 1] == 0) break;
+    if (ip_node_budget > 0 && (long long)H->n_nodes > ip_node_budget) { over_budget = true; break; }
     chunk = 3;
   }
   // ---- what the device did
@@ -765,6 +773,10 @@ int moip_ctx::solve_ip_chained(int cost, const double* srhs, const long long* ol
     have_inc = true; inc_val = H->inc_val;
     inc_x.assign(h_inc.p, h_inc.p + n);
   }
+  if (over_budget) {                     // drain the rounds still queued: the pool rows are reused by the next IP
+    MOIP_CUDA(cudaMemsetAsync(ctl->count, 0, sizeof(int) * 2, stream));
+    return MOIP_ERR_BUDGET;
+  }
   if (H->overflow) { chain_fallbacks += 1; return MOIP_OK; }      // the caller's loop solves the IP from the root, with this incumbent
   chain_rounds_avg[stage] += 0.125 * ((double)H->rounds_live - chain_rounds_avg[stage]);
   handled = true;
@@ -781,7 +793,9 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   const double sgn = dm.sgn;
   stats.ip_solved += 1;
   stage_ips[cur_stage] += 1;
-  long long ip_rounds = 0;
+  long long ip_rounds = 0, ip_nodes = 0;
+  static const long long explode_log = std::getenv("MOIP_EXPLODE_LOG") ? std::atoll(std::getenv("MOIP_EXPLODE_LOG")) : 0;
+  bool explode_said = false;
   out.status = MOIP_MIP_INFEASIBLE;
   out.x.clear();
   if (M.int_infeasible) return MOIP_OK;
@@ -932,6 +946,18 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     }
     const int B = (int)batch.size();
     if (B == 0) break;
+    ip_nodes += B;
+    if (explode_log > 0 && ip_nodes > explode_log && !explode_said) {
+      explode_said = true;
+      std::fprintf(stderr, "moip_b200: IP past %lld nodes: stage %d cost %d rhs [%g %g %g %g] incumbent %s%lld, open %zu, round %lld, node-LP cap %d\n", explode_log, cur_stage, cost,
+                   srhs[0], k > 1 ? srhs[1] : 0.0, k > 2 ? srhs[2] : 0.0, k > 3 ? srhs[3] : 0.0, have_inc ? "" : "none ", have_inc ? inc_val : 0LL, open.size(), ip_rounds, lp_cap);
+    }
+    if (ip_node_budget > 0 && ip_nodes > ip_node_budget) {     // given up: nothing is recorded, the caller decides what to do
+      for (auto& nd : batch) free_slots.push_back(nd.slot);
+      for (auto& nd : open) free_slots.push_back(nd.slot);
+      dbg_where.store(0, std::memory_order_relaxed);
+      return MOIP_ERR_BUDGET;
+    }
     stats.bb_nodes += B;
     stage_nodes[cur_stage] += B; stage_rounds[cur_stage] += 1; ++ip_rounds;
     dbg_where.store(2, std::memory_order_relaxed); dbg_rounds.store(ip_rounds, std::memory_order_relaxed); dbg_open.store((long long)open.size() + B, std::memory_order_relaxed);

@@ -213,6 +213,7 @@ struct moip_ctx {
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
   // ---- chained rounds (bbchain.h): the tree of an IP advances on the device, the host looks in once per chunk of rounds
+  long long ip_node_budget = 0;   // > 0: solve_ip gives up (MOIP_ERR_BUDGET) beyond this many nodes (moip_ctx_set_ip_node_budget)
   bool use_chain = true;       // MOIP_CHAIN=0: every round through the host (solve_ip's own loop)
   bool chain_debug = false;    // MOIP_CHAIN_DEBUG=1: synchronise after every launch and say which one failed
   int chain_q = 4096;          // pool rows per parity = widest tree level the device handles (MOIP_CHAIN_Q)

@@ -30,7 +30,7 @@ for spec in sys.argv[1:]:
         ips = [p["ips"] for p in pr]
         print(f"{spec}: {r['seconds']:.3f}s ok={r['matches_golden']} ips={r['ips']} node_lps={r['node_lps']} strips={r['strips']} "
               f"windows={[l.get('windows') for l in pr[0]['levels']]} level_s={[l['seconds'] for l in pr[0]['levels']]} "
-              f"ips/rank={min(ips)}..{max(ips)} cuts={sum(p['strips_cut_by_idle_workers'] for p in pr)} "
+              f"ips/rank={min(ips)}..{max(ips)} cuts={sum(p['strips_cut_by_idle_workers'] for p in pr)} postponed={sum(p['boxes_postponed'] for p in pr)} "
               f"solver_s/rank={min(p['solver_s'] for p in pr)}..{max(p['solver_s'] for p in pr)} "
               f"rec_rx={[l['records_received'] for l in pr[0]['levels']]}", flush=True)
 if world > 1:
