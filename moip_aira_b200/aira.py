@@ -36,6 +36,8 @@ class Dist:
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.device = device
         self.pg = None
+        Dist._jobs = getattr(Dist, "_jobs", 0) + 1      # every rank makes the same sequence of Dist objects: names job-wide keys
+        self._job = Dist._jobs
         if self.world > 1:
             import torch.distributed as dist
             if not dist.is_initialized():
@@ -82,7 +84,7 @@ class Dist:
         from torch.distributed import distributed_c10d
         store = distributed_c10d._get_default_store()
         self._seq = getattr(self, "_seq", 0) + 1          # every rank makes the same sequence of calls
-        key = "moip_strips_%d_%s" % (self._seq, name)
+        key = "moip_strips_%d_%d_%s" % (self._job, self._seq, name)
         return lambda: store.add(key, 1) - 1
 
 
@@ -168,23 +170,14 @@ class RecordExchange:
 
 # ------------------------------------------------------------------------------------ backends
 def default_workers():
-    """Solver contexts (= host threads) per GPU: MOIP_WORKERS, else as many spinning workers as this rank's share of the
-    host's cores carries (at most 16), or -- below 8 -- 24 workers that sleep on a blocking event while their round is on
-    the device (MOIP_SYNC=auto picks the wait mode from the same numbers).  Every worker drives its B&B rounds from its own host thread: ~40 us of CPU next to
-    ~400 us on the device per round, so a sleeping worker needs a tenth of a core.  Measured, 3AP n=30 front on one B200:
-    16 cores 16 spinning workers 6.3 s; 4 cores (taskset): 4 spinning 15.8 s, 12 spinning 17.0 s, 12 / 16 / 24 sleeping
-    9.6 / 8.6 / 7.5 s (profiles/r02_fronts.md)."""
+    """Solver contexts (= host threads) per GPU: MOIP_WORKERS, else 24.  Every worker drives the B&B of its own IPs from its own
+    host thread; with chained rounds (csrc/bbchain.h) that is a handful of launches and one wait per IP, so a worker needs a
+    fraction of a core, and the pool lets its workers sleep on a blocking event whenever they outnumber the cores this rank
+    may use (MOIP_SYNC=auto).  Measured, 3AP n=30 front on one B200 with 16 host cores: 16 spinning workers 6.6 s, 24 spinning
+    6.2 s, 24 sleeping 5.5 - 5.7 s, 32 spinning 6.2 s (profiles/r02_fronts.md)."""
     if os.environ.get("MOIP_WORKERS"):
         return int(os.environ["MOIP_WORKERS"])
-    ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 16
-    spare = cores // ranks_here - 2                       # Python + the exchange thread
-    if spare >= 14:
-        return 16
-    return spare if spare >= 8 else 24                    # (2 ranks on 24 cores: 10 spinning 4.7 s, 16 sleeping 5.5 s)
+    return 24
 
 
 class GpuBackend:

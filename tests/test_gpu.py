@@ -403,6 +403,35 @@ def test_pool_work_stealing(mb, tmp_path, name, strips, workers):
     pool.close()
 
 
+@pytest.mark.parametrize("name,env", [("ap3_12_1", {"MOIP_CHAIN": "0"}), ("ap3_12_1", {"MOIP_CHAIN_Q": "64"}),
+                                      ("kp4_25_1", {"MOIP_CHAIN": "0"}), ("kp4_25_1", {"MOIP_CHAIN_Q": "64"}),
+                                      ("ap3_15_1", {"MOIP_CHAIN_Q": "256", "MOIP_BB_LEVELS": "1"})])
+def test_chained_rounds_and_host_loop_agree(mb, tmp_path, monkeypatch, name, env):
+    """The B&B of an IP runs chained on the device (csrc/bbchain.h) or round by round through the host (MOIP_CHAIN=0); with a
+    small pool (MOIP_CHAIN_Q) tree levels outgrow it and those IPs are handed back to the host loop in mid-run.  Same front."""
+    path, want = _synthetic_case(name, tmp_path)
+    for a, v in env.items():
+        monkeypatch.setenv(a, v)
+    pool = mb.WorkerPool(mb.Problem(path), 0, 8)
+    assert pool.pareto_front(8) == want
+    pool.close()
+
+
+@pytest.mark.parametrize("name,boxes,wins", [("ap3_12_1", 16, 4), ("kp4_25_1", 16, 2), ("ap3_15_1", 32, 8), ("kp3_40_1", 12, 3)])
+def test_front_boxes_golden(mb, tmp_path, monkeypatch, name, boxes, wins):
+    """EPP strips crossed with windows on objective 1 (moip_worker::window, aira.epp_front): same front."""
+    from moip_aira_b200 import aira
+    path, want = _synthetic_case(name, tmp_path)
+    monkeypatch.setenv("MOIP_WINDOWS", str(wins))
+    monkeypatch.setenv("MOIP_WORKERS", "8")
+    be = aira.GpuBackend(path, device=0)
+    stats = []
+    front = aira.epp_front(be, aira.Dist(None), boxes, False, stats)
+    assert [tuple(r) for r in front] == want
+    assert stats[-1]["strips"] <= boxes and stats[-1]["windows"] >= 1
+    be.pool.close()
+
+
 def test_front_synthetic_vs_bruteforce(mb, tmp_path):
     """Synthetic assignment / knapsack instances against the solver-free brute-force front."""
     from oracle import aira_oracle as ao

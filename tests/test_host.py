@@ -219,7 +219,7 @@ class _OracleBackend:
 
     exchange = True            # offer the level's stores to aira.RecordExchange (the cross-rank cache sharing)
 
-    def run_strips(self, n_obj, strips, claim, share=0):
+    def run_strips(self, n_obj, strips, claim, share=0, windows=None):
         here, inf = ao.Solutions(self.k), ao.Solutions(self.k)
         self._stores, self._cursor, self._foreign = (inf, here), [0, 0], set()
         self.hits_on_foreign = getattr(self, "hits_on_foreign", 0)
@@ -240,7 +240,9 @@ class _OracleBackend:
             if t >= len(strips):
                 break
             a, b = strips[t]
-            w = self.mb.make_worker(self.k, n_obj=n_obj, split=True, split_start=a, split_stop=b, wid=t)
+            w = self.mb.make_worker(self.k, n_obj=n_obj, split=True, split_start=a, split_stop=b, wid=t,
+                                    window=windows[t] if windows is not None else None)
+            self.boxes_run = getattr(self, "boxes_run", 0) + (windows is not None)
             self.mb.optimise_with(self.k, self.sense, w, self.fs.lex_solve, find, insert)
             if getattr(self, "strip_delay", 0):
                 time.sleep(self.strip_delay)  # lets the exchange thread carry records between the ranks
@@ -343,11 +345,15 @@ sys.exit(rc)
 '''
 
 
-@pytest.mark.parametrize("stem,threads", [("4KP10", 4), ("3AP05", 2)])
-def test_aira_cli_epp_two_ranks_gloo(lib, examples, stem, threads, tmp_path):
+@pytest.mark.parametrize("stem,threads,windows", [("4KP10", 4, 0), ("3AP05", 2, 0), ("3AP05", 6, 3), ("4KP10", 8, 2), ("4AP05", 8, 4)])
+def test_aira_cli_epp_two_ranks_gloo(lib, examples, stem, threads, windows, tmp_path, monkeypatch):
     """world_size 2 over gloo: the strips of every EPP level are sharded over the ranks and the points
-    all-gathered between levels; rank 0 writes the same .out."""
+    all-gathered between levels; rank 0 writes the same .out.  windows > 0: the levels with three or more objectives are cut
+    into boxes (strips x windows on objective 1, moip_worker::window) dealt to the ranks as a Latin square."""
     from oracle.lpformat import parse_out
+    if windows:
+        monkeypatch.setenv("MOIP_WINDOWS", str(windows))
+        monkeypatch.setenv("MOIP_LOWER_STRIPS", "3")
     e = examples[stem]
     out = str(tmp_path / "o.out")
     script = tmp_path / "rank.py"
