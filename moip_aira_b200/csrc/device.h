@@ -89,6 +89,7 @@ struct LpBatch {
   // Fused B&B round (register-resident K1 only, `slot` set): the CTA that pulls a node first propagates it (K2,
   // k2_propagate.cuh) and, once its LP is solved, rounds the LP point three ways and verifies the candidates exactly
   // (what k4_round_verify_kernel does) -- one launch per round instead of three, the node's bounds read once.
+  int farkas;                 // plain batch on the register-resident K1: also test the Farkas certificate (k1_reg.cuh FARKAS)
   int fused;                  // 0 = plain LP batch (the f_* fields are ignored)
   const long long* f_obj_lo;  // [k] integer limits of the objective rows for the propagation (incl. the incumbent cut-off)
   const long long* f_obj_hi;

@@ -152,7 +152,10 @@ __device__ __forceinline__ int cost_of(const LpBatch& b, int node) { return b.co
 
 // FUSED: the B&B instantiation (LpBatch::fused): K2 propagation in front of the LP, K4 rounding/verification behind it.
 // The plain instantiation (batch API, bench `value`) carries none of that code, so its iteration loop keeps its registers.
-template <int NT, int CPT, int KD, int ELLW, int MINB, bool FUSED>
+// FARKAS: the termination test also evaluates the Farkas certificate (always in the B&B instantiation).  In the plain batch
+// instantiation it is a launch-time choice (LpBatch::farkas): its two extra sums change the register allocation of the
+// whole iteration loop (ptxas: 28 -> 40-56 bytes of spill loads), which costs a batch of feasible node LPs 5 %.
+template <int NT, int CPT, int KD, int ELLW, int MINB, bool FUSED, bool FARKAS>
 __global__ void __launch_bounds__(NT, MINB)
 k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lpr_log2) {
   constexpr int NW = NT / 32;
@@ -480,7 +483,8 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
         if (check_it) next_check += p.check_every;
         __syncthreads();                   // ytsh visible
         // pobj, dual (columns), dual (rows), primal residual^2 (unscaled), Farkas value (columns), sum of its |terms|
-        double aC[6] = {0, 0, 0, 0, 0, 0};
+        double aC[4] = {0, 0, 0, 0};
+        double aF[2] = {0, 0};             // (reduced on their own: six values in one reduction cost the iteration loop spills)
         double ytd[KD];
 #pragma unroll
         for (int d = 0; d < KD; ++d) ytd[d] = ytsh[msS + d];
@@ -496,25 +500,37 @@ k1_reg_kernel(const DevModel dm, const LpBatch b, const LpParams p, const int lp
           const double r = cj - g;
           aC[0] = fma(cj, xts_t[c * NT], aC[0]);
           aC[1] += (r > 0) ? r * bx.x : r * bx.y;
-          const double fk = (g < 0) ? -g * bx.x : -g * bx.y;        // the same bound with the objective dropped (Farkas)
-          aC[4] += fk; aC[5] += fabs(fk);
+          if (FARKAS) {
+            const double fk = (g < 0) ? -g * bx.x : -g * bx.y;      // the same bound with the objective dropped (Farkas)
+            aF[0] += fk; aF[1] += fabs(fk);
+          }
         }
         if (role & ROLE_LIVE) {
           if (r_yt > 0) aC[2] = -r_yt * r_nlo;
           else if (r_yt < 0) aC[2] = -r_yt * r_nhi;
-          aC[5] += fabs(aC[2]);
+          if (FARKAS) aF[1] += fabs(aC[2]);
           const double viol = dmax(0.0, dmax(r_sxt + r_nhi, -r_nlo - r_sxt)) / dm.dr_k[row];
           aC[3] = viol * viol;
         }
         // chained rounds: other CTAs lower the cutoff while this one runs -- one thread reads it, so that every thread of
         // the CTA takes the same way out of the loop
         if (FUSED && tid == 0) cold[COLD_CUTOFF] = b.cutoff ? *((volatile const double*)b.cutoff) : HUGE_VAL;
-        bsum<6, NT>(aC, redC, tid);
+        if (FUSED) {                       // (B&B instantiation: one reduction over all six)
+          double a6[6] = {aC[0], aC[1], aC[2], aC[3], aF[0], aF[1]};
+          bsum<6, NT>(a6, redC, tid);
+          aC[0] = a6[0]; aC[1] = a6[1]; aC[2] = a6[2]; aC[3] = a6[3]; aF[0] = a6[4]; aF[1] = a6[5];
+        } else {
+          bsum<4, NT>(aC, redC, tid);
+          if (FARKAS) {
+            __syncthreads();               // redC is read by every thread before it is written again
+            bsum<2, NT>(aF, redC, tid);
+          }
+        }
         const double pobj = aC[0], dobj = aC[1] + aC[2];
         // Farkas certificate: F(y) = min over the box of (-S^T y) x + (y+ lo - y- hi) <= 0 for every point that satisfies
         // the rows, so F(y) > 0 proves the node LP infeasible -- long before the Lagrangian bound (the same sum plus the
         // objective) climbs past the objective's maximum on the box.  The margin is 1000x the rounding error of the sum.
-        const bool farkas = aC[4] + aC[2] > 1e-9 * aC[5] + 1e-9;
+        const bool farkas = FARKAS && aF[0] + aC[2] > 1e-9 * aF[1] + 1e-9;
         double best_lb = cold[COLD_BEST_LB];
         const double obj_upper = cold[COLD_OBJ_UPPER], kkt_binv = cold[COLD_KKT_BINV];
         if (p.fixed_iters > 0) best_lb = dobj;
@@ -751,9 +767,9 @@ inline int env_int(const char* name, int dflt) {
   return v ? std::atoi(v) : dflt;
 }
 
-template <int NT, int CPT, int KD, int ELLW, int MINB, bool FUSED>
+template <int NT, int CPT, int KD, int ELLW, int MINB, bool FUSED, bool FARKAS>
 int launch_reg_f(const DevModel& dm, const LpBatch& b, LpParams p, int num_sms, cudaStream_t st) {
-  auto kern = k1_reg_kernel<NT, CPT, KD, ELLW, MINB, FUSED>;
+  auto kern = k1_reg_kernel<NT, CPT, KD, ELLW, MINB, FUSED, FARKAS>;
   const size_t prod_len = ((size_t)dm.msS * dm.RWP + 2 + 1) & ~(size_t)1;
   const size_t smem = kYshBytes + sizeof(double) * (prod_len + 256 + 8 + COLD_N + 2 + (size_t)16 * (NT / 32) + 2 +
                                                     (size_t)4 * NT * CPT + (size_t)(KD + 2) * NT);
@@ -792,9 +808,10 @@ template <int NT, int CPT, int KD, int ELLW, int MINB>
 int launch_reg(const DevModel& dm, const LpBatch& b, const LpParams& p, int num_sms, cudaStream_t st) {
   if (b.fused) {
     if (!b.slot && !b.B_dev) return MOIP_ERR_ARG;
-    return launch_reg_f<NT, CPT, KD, ELLW, MINB, true>(dm, b, p, num_sms, st);
+    return launch_reg_f<NT, CPT, KD, ELLW, MINB, true, true>(dm, b, p, num_sms, st);
   }
-  return launch_reg_f<NT, CPT, KD, ELLW, MINB, false>(dm, b, p, num_sms, st);
+  if (b.farkas) return launch_reg_f<NT, CPT, KD, ELLW, MINB, false, true>(dm, b, p, num_sms, st);
+  return launch_reg_f<NT, CPT, KD, ELLW, MINB, false, false>(dm, b, p, num_sms, st);
 }
 
 // shape dispatch for one KD (one translation unit per KD keeps the build parallel)

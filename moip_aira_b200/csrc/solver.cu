@@ -151,6 +151,7 @@ extern "C" int moip_ctx_create(moip_model* m, int device, void* stream, moip_ctx
   c->use_points = env_int("MOIP_POINT_STORE", 1) != 0;
   c->use_fused = env_int("MOIP_FUSED_ROUND", 1) != 0;
   c->use_chain = env_int("MOIP_CHAIN", 1) != 0;
+  c->batch_farkas = env_int("MOIP_K1_BATCH_FARKAS", 0) != 0;
   c->chain_q = std::max(64, env_int("MOIP_CHAIN_Q", 4096));
   c->chain_debug = env_int("MOIP_CHAIN_DEBUG", 0) != 0;
   c->k3_poll = env_int("MOIP_K3_POLL", 1) != 0;
@@ -335,6 +336,7 @@ extern "C" int moip_lp_batch_run(moip_ctx* c, const moip_lp_params* params) {
   b.warm_x = nullptr; b.warm_y = nullptr; b.out_x = c->b_x.p; b.out_y = nullptr;
   b.primal_obj = c->b_pobj.p; b.dual_bound = c->b_dbound.p; b.status = c->b_status.p; b.iters = c->b_iters.p;
   b.branch_var = c->b_branch.p; b.branch_val = nullptr; b.skip = nullptr; b.slot = nullptr; b.rc_fix = 0;
+  b.farkas = c->batch_farkas ? 1 : 0;
   b.cost_stride = 1; b.rhs_stride = d.k;
   b.cutoff = c->b_cutoff.p; b.work_counter = c->b_counter.p;
   LpParams p{};
@@ -1005,6 +1007,7 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
     kmark(2);
     LpBatch b{};
     b.B = B; b.rhs = d_rhs; b.lb = pool.lb; b.ub = pool.ub; b.slot = d_ids; b.rc_fix = have_inc ? 1 : 0;
+    b.farkas = 1;
     if (fused) {
       b.fused = 1; b.f_obj_lo = d_olo; b.f_obj_hi = d_ohi; b.f_max_rounds = 16; b.f_flag = d_flag; b.f_leaf_obj = d_leaf;
       b.f_xr = r_xr.p; b.f_cand_obj = d_cobj; b.f_cand_feas = d_cfeas; b.f_first_free = d_ff;

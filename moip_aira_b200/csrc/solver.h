@@ -213,6 +213,8 @@ struct moip_ctx {
   double prof_t[7] = {0, 0, 0, 0, 0, 0, 0};   // MOIP_PROFILE_ROUNDS: enqueue / device wait / host seconds, rounds, nodes
 
   // ---- chained rounds (bbchain.h): the tree of an IP advances on the device, the host looks in once per chunk of rounds
+  bool batch_farkas = false;      // moip_lp_batch_* on the register-resident K1: Farkas certificate in the termination test (MOIP_K1_BATCH_FARKAS=1);
+                                  // off, infeasible node LPs are recognised by the Lagrangian bound alone, as in round 1
   long long ip_node_budget = 0;   // > 0: solve_ip gives up (MOIP_ERR_BUDGET) beyond this many nodes (moip_ctx_set_ip_node_budget)
   bool use_chain = true;       // MOIP_CHAIN=0: every round through the host (solve_ip's own loop)
   bool chain_debug = false;    // MOIP_CHAIN_DEBUG=1: synchronise after every launch and say which one failed
