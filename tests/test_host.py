@@ -486,3 +486,27 @@ def test_generator_boxes_enumerate_the_front(lib, tmp_path, kind, k, n, seed, st
             lib.optimise_with(k, 0 if is_min else 1, w, solve, find, insert)
             found |= {tuple(r.result) for r in s.store if not r.infeasible}
     assert sorted(found, reverse=True) == want
+
+
+def test_window_edges_and_counts(monkeypatch):
+    """aira.window_edges: the windows tile the whole axis (first one open towards "free", last one without a far edge, one
+    unit between a far edge and the next near edge), for both senses; aira.windows_for: powers of two that leave 8 strips."""
+    from moip_aira_b200 import aira
+    vals = sorted({3 * i + (i % 5) for i in range(40)})
+    for is_min in (True, False):
+        ed = aira.window_edges(vals, 4, is_min)
+        assert 2 <= len(ed) <= 4
+        assert ed[0][0] == (1e20 if is_min else -1e20) and ed[-1][1] == (-1e20 if is_min else 1e20)
+        for (n0, f0), (n1, f1) in zip(ed, ed[1:]):
+            assert (f0 == n1 + 1) if is_min else (f0 == n1 - 1)
+            assert (n0 > n1) if is_min else (n0 < n1)
+        # every value belongs to exactly one window
+        for v in vals:
+            owners = [i for i, (ne, fa) in enumerate(ed) if ((v <= ne and v >= fa) if is_min else (v >= ne and v <= fa))]
+            assert len(owners) == 1, (v, ed)
+    assert aira.window_edges([1, 2, 3], 4, True) == [(1e20, -1e20)]            # too few values: one window
+    monkeypatch.delenv("MOIP_WINDOWS", raising=False)
+    assert aira.windows_for(2, 768, 8) == 1
+    assert [aira.windows_for(3, t, 1) for t in (8, 16, 24, 96, 192, 768)] == [1, 2, 2, 8, 16, 16]
+    monkeypatch.setenv("MOIP_WINDOWS", "1")
+    assert aira.windows_for(4, 768, 8) == 1

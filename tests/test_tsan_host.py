@@ -33,7 +33,7 @@ def test_host_code_is_race_free(tsan_bin, tmp_path, kind, n, k, seed, reps):
     from moip_aira_b200 import instances
     path = str(tmp_path / "m.lp")
     (instances.write_ap if kind == "ap" else instances.write_kp)(path, n, k, seed)
-    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0", MOIP_BOX_BUDGET="1")
     r = subprocess.run([tsan_bin, path, str(reps), "12"], capture_output=True, text=True, env=env, timeout=900)
     assert "ThreadSanitizer" not in r.stderr, r.stderr[-4000:]
     assert r.returncode == 0 and "TSAN_HOST_OK" in r.stdout, (r.stdout[-500:], r.stderr[-2000:])

@@ -174,6 +174,12 @@ int moip_ctx::solve_ip(int cost, const double* srhs, const std::vector<int>* inc
   out.status = MOIP_MIP_INFEASIBLE;
   out.x.clear();
   if (M.int_infeasible) return MOIP_OK;
+  // node budget (moip_ctx_set_ip_node_budget; the box scheduler's postponement): a tiny budget makes every other budgeted
+  // IP give up, so that the put-back / retry path of run_boxes is exercised
+  if (ip_node_budget > 0 && ip_node_budget <= 8) {
+    static std::atomic<unsigned> flip{0};
+    if (flip.fetch_add(1) % 2 == 0) return MOIP_ERR_BUDGET;
+  }
   std::vector<long long> olo(k, LLONG_MIN), ohi(k, LLONG_MAX);
   for (int o = 0; o < k; ++o) {
     if (std::fabs(srhs[o]) >= 1e19) continue;

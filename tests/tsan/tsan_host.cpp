@@ -5,6 +5,7 @@
 //   (2) two pools ("ranks") solving interleaved strips of one level while a third thread carries cache records between
 //       them (moip_pool_export_records / moip_pool_import_records, the path aira.RecordExchange drives);
 //   (3) moip_pool_synergistic_front: W = k cooperative workers exchanging limits;
+//   (5) moip_pool_run_boxes_claim: strips x windows, postponed boxes (MOIP_BOX_BUDGET=1);
 //   (4) the link-level CPLEX seam (seam1/cpx_shim.cpp): T threads, one environment + problem object each, the call
 //       sequence of the reference's solve() (src/aira.cpp:452-536).
 // Every result is compared with the single-context run; the whole programme is repeated argv[2] times.
@@ -50,7 +51,7 @@ int main(int argc, char** argv) {
   // strip edges of the top level: range of the last objective over the front
   int lo = INT32_MAX, hi = INT32_MIN;
   for (auto& r : want) { lo = std::min(lo, r[k - 1]); hi = std::max(hi, r[k - 1]); }
-  long long steals = 0;
+  long long steals = 0, postponed = 0;
   for (int rep = 0; rep < reps; ++rep) {
     // (1) pool, strips < workers
     moip_pool* p = nullptr;
@@ -99,6 +100,30 @@ int main(int argc, char** argv) {
     CHECK(got == want);
     int64_t ex = 0, im = 0;
     CHECK(moip_pool_exchange_counts(p, &ex, &im) == MOIP_OK);
+    // (5) boxes: strips of the last objective x windows on objective 1, more workers than boxes at the end (cuts), and --
+    // with MOIP_BOX_BUDGET=1 in the environment -- boxes whose first subproblem "runs out of budget" are put back and retried
+    if (k >= 3) {
+      int lo1 = INT32_MAX, hi1 = INT32_MIN;
+      for (auto& r : want) { lo1 = std::min(lo1, r[1]); hi1 = std::max(hi1, r[1]); }
+      const int SB = 2 + rep % 2, WN = 3;
+      std::vector<double> sb(2 * SB), bs, bw;
+      CHECK(moip_split_strips(info.sense, hi + 1, lo - 1, SB, 0, sb.data()) == MOIP_OK);
+      const bool is_min = info.sense == MOIP_SENSE_MIN;
+      const double big = 1e20;
+      for (int s_ = 0; s_ < SB; ++s_)
+        for (int w_ = 0; w_ < WN; ++w_) {
+          // window w_ of WN on [lo1, hi1]: near edge free for the first, no far edge for the last
+          const double c_hi = lo1 + (double)(hi1 - lo1) * (WN - w_) / WN, c_lo = lo1 + (double)(hi1 - lo1) * (WN - w_ - 1) / WN;
+          double near_e, far_e;
+          if (is_min) { near_e = w_ == 0 ? big : std::floor(c_hi); far_e = w_ == WN - 1 ? -big : std::floor(c_lo) + 1; }
+          else { near_e = w_ == WN - 1 ? -big : std::floor(c_lo) + 1; far_e = w_ == 0 ? big : std::floor(c_hi); }
+          bs.push_back(sb[2 * s_]); bs.push_back(sb[2 * s_ + 1]);
+          bw.push_back(near_e); bw.push_back(far_e);
+        }
+      CHECK(moip_pool_run_boxes_claim(p, k, SB * WN, bs.data(), bw.data(), nullptr, nullptr, rows.data(), cap, &nrows) == MOIP_OK);
+      CHECK(rows_to_front(rows, nrows, k) == want);
+      postponed += moip_pool_boxes_postponed(p);
+    }
     moip_pool_destroy(q);
     moip_pool_destroy(p);
   }
@@ -152,6 +177,6 @@ int main(int argc, char** argv) {
   }
   moip_ctx_destroy(c0);
   moip_model_free(m);
-  std::printf("TSAN_HOST_OK front=%zu reps=%d workers=%d strips_cut_by_idle_workers=%lld\n", want.size(), reps, workers, steals);
+  std::printf("TSAN_HOST_OK front=%zu reps=%d workers=%d strips_cut_by_idle_workers=%lld boxes_postponed=%lld\n", want.size(), reps, workers, steals, postponed);
   return 0;
 }
