@@ -1034,12 +1034,48 @@ int epp_level_pool(moip_pool* p, int n_obj, int num_threads, int split_normal, s
     for (auto& s : lower) smallest = std::min(smallest, s[n_obj - 1]);
     if (biggest == smallest) smallest = INT_MIN;
   }
-  std::vector<double> ss(2 * (size_t)num_threads);
-  if ((rc = moip_split_strips(sense, biggest, smallest, num_threads, split_normal, ss.data()))) return rc;
+  // Boxes (moip_worker::window; the same rule as aira.windows_for / aira.window_edges): with 16 or more entries the level is
+  // cut both ways -- nwin windows on objective 1 (the largest power of two <= 16 that leaves 8 strips; edges = quantiles of
+  // that objective over the level below) times num_threads / nwin strips.  MOIP_WINDOWS=<n> fixes nwin (1 = strips only).
+  int nwin = 1;
+  if (n_obj >= 3) {
+    if (const char* e = std::getenv("MOIP_WINDOWS")) nwin = std::max(1, std::min(std::atoi(e), num_threads));
+    else while (nwin < 16 && num_threads / (nwin * 2) >= 8) nwin *= 2;
+  }
+  std::vector<double> near_edge;                       // near edges of the windows, first one "free"
+  if (nwin > 1) {
+    std::vector<int> vals;
+    for (auto& s : lower) vals.push_back(s[1]);
+    std::sort(vals.begin(), vals.end());
+    vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+    if ((int)vals.size() < 2 * nwin) nwin = 1;
+    else {
+      std::vector<int> cuts;
+      for (int i = 1; i < nwin; ++i) cuts.push_back(vals[vals.size() * (size_t)i / nwin]);
+      cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+      near_edge.push_back(is_min ? kInf : -kInf);
+      if (is_min) for (auto it = cuts.rbegin(); it != cuts.rend(); ++it) near_edge.push_back((double)*it);
+      else for (int c : cuts) near_edge.push_back((double)c);
+      nwin = (int)near_edge.size();
+    }
+  }
+  const int nstrips = nwin > 1 ? std::max(1, num_threads / nwin) : num_threads;
+  std::vector<double> ss(2 * (size_t)nstrips);
+  if ((rc = moip_split_strips(sense, biggest, smallest, nstrips, split_normal, ss.data()))) return rc;
+  std::vector<double> bs, bw;
+  if (nwin > 1)
+    for (int t = 0; t < nstrips; ++t)
+      for (int w = 0; w < nwin; ++w) {
+        bs.push_back(ss[2 * t]); bs.push_back(ss[2 * t + 1]);
+        bw.push_back(near_edge[w]);                     // a window ends one unit before the next one starts
+        bw.push_back(w + 1 < nwin ? near_edge[w + 1] + (is_min ? 1.0 : -1.0) : (is_min ? -kInf : kInf));
+      }
   int cap = 1 << 14, nrows = 0;
   std::vector<int> rows((size_t)cap * k);
   for (;;) {
-    if ((rc = moip_pool_run_strips(p, n_obj, num_threads, ss.data(), rows.data(), cap, &nrows))) return rc;
+    if (nwin > 1) rc = moip_pool_run_boxes_claim(p, n_obj, nstrips * nwin, bs.data(), bw.data(), nullptr, nullptr, rows.data(), cap, &nrows);
+    else rc = moip_pool_run_strips(p, n_obj, num_threads, ss.data(), rows.data(), cap, &nrows);
+    if (rc) return rc;
     if (nrows <= cap) break;
     cap = nrows; rows.assign((size_t)cap * k, 0);       // (re-solves; only for fronts beyond 16k rows)
   }

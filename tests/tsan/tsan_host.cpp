@@ -59,6 +59,9 @@ int main(int argc, char** argv) {
     CHECK(moip_pool_pareto_front(p, 2 + rep % 3, 0, rows.data(), cap, &nrows) == MOIP_OK);
     CHECK(rows_to_front(rows, nrows, k) == want);
     steals += moip_pool_strips_stolen(p);
+    // (1b) 16 or more entries: the levels with three or more objectives are cut into boxes (epp_level_pool)
+    CHECK(moip_pool_pareto_front(p, 16 + rep % 9, 0, rows.data(), cap, &nrows) == MOIP_OK);
+    CHECK(rows_to_front(rows, nrows, k) == want);
     // (3) cooperative workers
     CHECK(moip_pool_synergistic_front(p, k, rows.data(), cap, &nrows) == MOIP_OK);
     CHECK(rows_to_front(rows, nrows, k) == want);
