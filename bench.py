@@ -8,9 +8,10 @@
     bound, status, iterations inside the timed region).  `roofline` is SURVEY.md section 8d's HBM figure (algorithmic bytes
     16(n+m)+ceil(n/4)+8k+4 per node-iteration x the iterations the launch executed / the launch's CUDA-event duration,
     against the measured copy bandwidth in MEASURED_PEAKS.json) plus the resource that actually binds, the fp64 pipe.
-(2) Pareto-front time-to-solve (`time_to_front_s`): the shipped Examples, synthetic 3AP n=30 and 4KP n=40 with the EPP
-    strips sharded over the N ranks (strong scaling), the cooperative ("synergistic") workers one per rank, and the
-    Examples' `--split -t 8`; every front is checked against its committed golden.
+(2) Pareto-front time-to-solve (`time_to_front_s`): the shipped Examples, synthetic 3AP n=30 and 4KP n=40 with the top
+    EPP level cut into boxes (strips of the last objective x windows on objective 1; four per solver context)
+    sharded over the N ranks (strong scaling), the cooperative ("synergistic") workers one per rank, and the Examples'
+    `--split -t 8`; every front is checked against its committed golden.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--workload ap30|kp40] [--no-fronts]
 
