@@ -54,6 +54,12 @@ def test_seam_primitives_validate_arguments_and_need_a_gpu(lib, examples):
     h = C.c_void_p()
     assert L.moip_ctx_create_own_stream(None, 0, C.byref(h)) == 1
     assert L.moip_ctx_create_own_stream(pr._h, 0, None) == 1
+    n = C.c_int(0)
+    ss = (C.c_double * 2)(10.0, 0.0)
+    assert L.moip_pool_run_boxes_claim(None, 3, 1, ss, ss, lib.CLAIM_FN(0), None, None, 0, C.byref(n)) == 1   # no pool
+    assert L.moip_pool_run_boxes_claim(None, 3, 1, ss, None, lib.CLAIM_FN(0), None, None, 0, C.byref(n)) == 1  # boxes need windows
+    assert L.moip_ctx_set_ip_node_budget(None, 10) == 1
+    assert L.moip_pool_boxes_postponed(None) == -1
     if torch.cuda.is_available():
         assert L.moip_device_count() >= 1
     else:
